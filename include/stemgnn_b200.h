@@ -1,0 +1,184 @@
+/*
+ * stemgnn_b200 — C ABI of the B200 (sm_100a) implementation of StemGNN's per-step hot path.
+ *
+ * The reference (microsoft/StemGNN @ dc7dea68) has NO native code and NO FFI: its hot path is
+ * `models/base_model.py` calling ATen.  This header is therefore the NEW seam that sits
+ * directly under `models.base_model.Model.forward` (base_model.py:167-179) and the autograd
+ * backward that `handler.train` triggers (handler.py:161-165).  Each entry point names the
+ * reference lines it replaces.
+ *
+ * Conventions:
+ *   - every tensor argument is a raw DEVICE pointer to contiguous row-major fp32 unless stated;
+ *     dimensions are explicit ints; the CALLER owns every buffer (inputs, outputs, workspace);
+ *     the library never allocates, frees or retains device pointers past the call;
+ *   - every call takes a cudaStream_t (passed as void*) and is asynchronous on it;
+ *   - return value: 0 = ok, nonzero = error (invalid shape, unsupported size, launch failure);
+ *     a message is available from stemgnn_last_error() (thread-local); nothing throws/aborts;
+ *   - no global mutable state except per-device cached function attributes;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef STEMGNN_B200_H_
+#define STEMGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define STEMGNN_ABI_VERSION 1
+#define STEMGNN_K 4            /* Chebyshev order "3 + 1", base_model.py:23 */
+#define STEMGNN_MAX_STACK 2    /* Model.forward hard-codes result[0] + result[1], base_model.py:174 */
+
+typedef void* stemgnn_stream_t; /* cudaStream_t */
+
+/* Problem dimensions.  T = multi*W, d = 4*T. */
+typedef struct {
+  int B;      /* batch (windows) */
+  int N;      /* nodes = `units` */
+  int W;      /* time_step / window_size */
+  int H;      /* horizon */
+  int multi;  /* multi_layer */
+} stemgnn_dims_t;
+
+/* Parameters of one StockBlockLayer (base_model.py:17-44); same tensors as the reference
+ * state_dict entries `stock_block.<i>.*`.  glu_* index g: GLUs[g], g even = real chain, odd = imag. */
+typedef struct {
+  const float* weight;            /* (1,4,1,T,T)            base_model.py:23 */
+  const float* forecast_w;        /* (T,T)                  :27 */
+  const float* forecast_b;        /* (T)                        */
+  const float* forecast_result_w; /* (W,T)                  :28 */
+  const float* forecast_result_b; /* (W)                        */
+  const float* backcast_w;        /* (W,T) block 0 only     :30 (NULL for block 1) */
+  const float* backcast_b;        /* (W)                        */
+  const float* shortcut_w;        /* (W,W)                  :31 */
+  const float* shortcut_b;        /* (W)                        */
+  const float* glu_left_w[6];     /* (d,4W) g<2, else (d,d) :33-44 */
+  const float* glu_left_b[6];     /* (d) */
+  const float* glu_right_w[6];
+  const float* glu_right_b[6];
+} stemgnn_block_params_t;
+
+/* All parameters of Model (base_model.py:79-104). */
+typedef struct {
+  const float* weight_key;    /* (N,1)   :88 */
+  const float* weight_query;  /* (N,1)   :90 */
+  const float* gru_w_ih;      /* (3N,W)  :92  gate order [r,z,n] */
+  const float* gru_w_hh;      /* (3N,N)      */
+  const float* gru_b_ih;      /* (3N)        */
+  const float* gru_b_hh;      /* (3N)        */
+  stemgnn_block_params_t block[STEMGNN_MAX_STACK];
+  const float* fc0_w;         /* (W,W)   :98  */
+  const float* fc0_b;         /* (W)          */
+  const float* fc2_w;         /* (H,W)   :100 */
+  const float* fc2_b;         /* (H)          */
+} stemgnn_params_t;
+
+/* Same layout, mutable: gradient buffers (ACCUMULATED into, like autograd's .grad). */
+typedef struct {
+  float* weight; float* forecast_w; float* forecast_b; float* forecast_result_w;
+  float* forecast_result_b; float* backcast_w; float* backcast_b; float* shortcut_w;
+  float* shortcut_b; float* glu_left_w[6]; float* glu_left_b[6]; float* glu_right_w[6];
+  float* glu_right_b[6];
+} stemgnn_block_grads_t;
+
+typedef struct {
+  float* weight_key; float* weight_query; float* gru_w_ih; float* gru_w_hh; float* gru_b_ih;
+  float* gru_b_hh; stemgnn_block_grads_t block[STEMGNN_MAX_STACK];
+  float* fc0_w; float* fc0_b; float* fc2_w; float* fc2_b;
+} stemgnn_grads_t;
+
+/* Options of one forward call. */
+typedef struct {
+  float leaky_alpha;        /* LeakyReLU slope of the attention, base_model.py:102 (0.2) */
+  float dropout_p;          /* base_model.py:103 (0.5); only used when training != 0 */
+  int training;             /* 0: eval (no dropout, nothing saved for backward) */
+  uint64_t dropout_seed;    /* Philox key: the keep-mask of element (b,i,j) is a pure function */
+  uint64_t dropout_offset;  /*   of (seed, offset, b, i, j) and is regenerated in backward */
+  const uint8_t* dropout_mask; /* optional explicit keep-mask (B,N,N) of {0,1}; overrides Philox */
+  int gemm_mode;            /* 0 = auto (tcgen05 TF32 for the GLU chain when available),
+                               1 = force fp32 FFMA everywhere, 2 = force tcgen05 TF32 */
+} stemgnn_fwd_opts_t;
+
+/* ---- library ------------------------------------------------------------------------ */
+int stemgnn_version(void);                 /* STEMGNN_ABI_VERSION */
+const char* stemgnn_last_error(void);      /* thread-local, "" if none */
+int stemgnn_device_ok(void);               /* 1 if a usable sm_100 device is current, else 0 */
+
+/* Bytes of caller-provided workspace needed by stemgnn_model_forward / _backward for `dims`.
+ * The SAME buffer must be passed to the backward of a training forward (it holds the saved
+ * activations); eval forwards may reuse one buffer across calls. */
+size_t stemgnn_workspace_bytes(const stemgnn_dims_t* dims, int training);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* Model.forward (base_model.py:167-179).
+ *   x        (B,W,N)  in
+ *   forecast (B,H,N)  out   [(B,1,N) when H==1 — same memory layout]
+ *   attention(N,N)    out   symmetrised batch-mean attention (base_model.py:143)
+ *   mul_L    (4,N,N)  out, optional (NULL to skip): Chebyshev stack (base_model.py:148) */
+int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
+                          const stemgnn_fwd_opts_t* opts, const float* x, float* forecast,
+                          float* attention, float* mul_L, void* workspace, size_t workspace_bytes,
+                          stemgnn_stream_t stream);
+
+/* Backward of stemgnn_model_forward for loss L (autograd through base_model.py:136-179, as
+ * triggered by handler.py:164).  Needs the workspace of the matching training forward.
+ *   d_forecast (B,H,N) in; d_attention (N,N) in or NULL (handler.py discards attention);
+ *   grads: every non-NULL pointer is accumulated into (+=); d_x (B,W,N) out or NULL. */
+int stemgnn_model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
+                           const stemgnn_fwd_opts_t* opts, const float* x,
+                           const float* d_forecast, const float* d_attention,
+                           const stemgnn_grads_t* grads, float* d_x, void* workspace,
+                           size_t workspace_bytes, stemgnn_stream_t stream);
+
+/* ---- stage-level entry points (used by the Python mirror of the reference's methods and by
+ *      the parity tests; same kernels as the fused path) ------------------------------------ */
+/* nn.GRU over the node axis + key/query contraction (base_model.py:137,154-155).
+ *   x (B,W,N) -> key (B,N), query (B,N); gru_out (N,B,N) optional (NULL to skip).
+ *   path: 0 = auto, 1 = force the generic (per-step launch) path, 2 = force the cluster path. */
+int stemgnn_gru_keyquery_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
+                                 const float* x, float* key, float* query, float* gru_out,
+                                 int path, void* workspace, size_t workspace_bytes,
+                                 stemgnn_stream_t stream);
+
+/* softmax attention -> batch mean -> degree -> symmetrise -> normalised Laplacian -> Chebyshev
+ * stack (base_model.py:156-161, 140-148, 121-134).  key,query (B,N) -> attention (N,N), mul_L (4,N,N). */
+int stemgnn_graph_forward(const stemgnn_dims_t* dims, const stemgnn_fwd_opts_t* opts,
+                          const float* key, const float* query, float* attention, float* mul_L,
+                          void* workspace, size_t workspace_bytes, stemgnn_stream_t stream);
+
+/* StockBlockLayer.forward (base_model.py:61-75).  x_bnw (B,N,W), mul_L (4,N,N) ->
+ * forecast (B,N,W), backcast (B,N,W) (block 0 only; pass NULL for block 1). */
+int stemgnn_block_forward(const stemgnn_dims_t* dims, const stemgnn_block_params_t* bp,
+                          int stack_idx, int gemm_mode, const float* x_bnw, const float* mul_L,
+                          float* forecast, float* backcast, void* workspace,
+                          size_t workspace_bytes, stemgnn_stream_t stream);
+
+/* StockBlockLayer.spe_seq_cell (base_model.py:46-59).  gfted (B,4,N,W) -> iffted (B,4,N,T). */
+int stemgnn_spe_seq_cell_forward(const stemgnn_dims_t* dims, const stemgnn_block_params_t* bp,
+                                 int gemm_mode, const float* gfted, float* iffted, void* workspace,
+                                 size_t workspace_bytes, stemgnn_stream_t stream);
+
+/* C[M,N] = alpha * A(M,K) * B(K,N) + beta * C  on the library's fp32 FFMA2 GEMM (test hook).
+ * a_kmajor: 0 -> A[m*lda+k], 1 -> A[k*lda+m];  b_nk: 1 -> B[n*ldb+k] (nn.Linear weight), 0 -> B[k*ldb+n]. */
+int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int a_kmajor,
+                  const float* B, int ldb, int b_nk, float beta, float* C, int ldc,
+                  stemgnn_stream_t stream);
+
+/* out[M,N] = (A W_l^T + b_l) * sigmoid(A W_r^T + b_r)  (GLU, base_model.py:12-13) on the tcgen05
+ * TF32 tensor-core kernel (use_tc=1) or the fp32 FFMA2 kernel (use_tc=0).  A (M,K) lda; W (N,K). */
+int stemgnn_glu_gemm(int M, int N, int K, const float* A, int lda, const float* Wl, const float* bl,
+                     const float* Wr, const float* br, float* out, int ldo, int use_tc,
+                     stemgnn_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEMGNN_B200_H_ */

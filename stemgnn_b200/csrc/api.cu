@@ -1,0 +1,386 @@
+// C ABI of stemgnn_b200 (see include/stemgnn_b200.h): workspace carving + forward orchestration.
+// Every kernel is launched on the caller's stream; nothing here allocates device memory.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "internal.cuh"
+
+namespace sg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void clear_error() { g_err[0] = 0; }
+
+// ---- workspace layout (offsets in floats, 256-byte aligned) -------------------------------------
+Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
+  Workspace ws = {};
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += (n + 63) / 64 * 64;
+    return p;
+  };
+  const size_t B = dm.B, N = dm.N, W = dm.W, T = (size_t)dm.multi * dm.W, d = 4 * T, R = B * N;
+  ws.xs = take(N * B * W);
+  ws.x_bnw = take(R * W);
+  ws.key = take(R);
+  ws.query = take(R);
+  ws.qmax = take(B);
+  ws.a_raw = take(N * N);
+  ws.deg = take(N);
+  ws.mul_L = take(4 * N * N);
+  ws.attention = take(N * N);
+  ws.gru_scratch = take(2 * R);
+  ws.row_m = training ? take(R) : nullptr;
+  ws.row_zinv = training ? take(R) : nullptr;
+  ws.h_all = training ? take(N * R) : nullptr;
+  for (int i = 0; i < STEMGNN_MAX_STACK; ++i) {
+    BlockWs& b = ws.blk[i];
+    b.G = take(R * 4 * W);              // 3W columns on the model path, 4W for the stage API
+    b.w1f = take(4 * d * 4 * W);
+    b.ic = take(2 * T * T);
+    b.ri = take(8 * T * T);
+    b.wout = take(8 * T * (T + W));
+    b.act1 = take(2 * R * d);
+    b.act2 = take(2 * R * d);
+    b.act3 = take(R * 2 * d);
+    b.pre = take(R * (T + W));
+    b.forecast = take(R * W);
+    b.bc_bnw = take(R * W);
+    b.bc_bwn = take(R * W);
+    for (int g = 0; g < 6; ++g) {
+      b.save_l[g] = training ? take(R * d) : nullptr;
+      b.save_s[g] = training ? take(R * d) : nullptr;
+    }
+    b.fs = training ? take(R * T) : nullptr;
+  }
+  ws.floats = off;
+  return ws;
+}
+
+static int check_dims(const stemgnn_dims_t* dm) {
+  SG_CHECK(dm != nullptr, "dims is null");
+  SG_CHECK(dm->B > 0 && dm->N > 0 && dm->W > 0 && dm->H > 0 && dm->multi > 0,
+           "invalid dims B=%d N=%d W=%d H=%d multi=%d", dm->B, dm->N, dm->W, dm->H, dm->multi);
+  SG_CHECK(dm->W <= 64 && dm->H <= 64, "W=%d / H=%d above the supported 64", dm->W, dm->H);
+  SG_CHECK((long long)dm->B * dm->N * dm->N < (1ll << 40), "problem too large");
+  return 0;
+}
+
+static int check_ws(const stemgnn_dims_t* dm, int training, void* ws, size_t bytes) {
+  SG_CHECK(ws != nullptr, "workspace is null");
+  SG_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  const size_t need = stemgnn_workspace_bytes(dm, training);
+  SG_CHECK(bytes >= need, "workspace too small: %zu < %zu bytes", bytes, need);
+  return 0;
+}
+
+// ---- GLU layer dispatch: tcgen05 TF32 or fp32 FFMA2 ------------------------------------------------
+int glu_layer(int M, int N, int K, const float* A, int lda, const float* Wl, const float* bl,
+              const float* Wr, const float* br, float* out, int ldo, float* save_l, float* save_s,
+              int gemm_mode, cudaStream_t st) {
+  if (gemm_mode != 1) {
+    const int rc = glu_gemm_tc(M, N, K, A, lda, Wl, bl, Wr, br, out, ldo, save_l, save_s, N, st);
+    if (rc == 0) return 0;
+    if (rc > 0) return rc;
+    SG_CHECK(gemm_mode != 2, "tcgen05 GLU GEMM does not support M=%d N=%d K=%d lda=%d", M, N, K, lda);
+  }
+  GemmOperands g = {A, lda, 0, Wl, K, 0, Wr, M, N, K};
+  EpiGlu epi = {out, ldo, 0, bl, br, 0, save_l, save_s, N, 0};
+  return launch_sgemm<false, true, true>(g, epi, 1, st, "glu_gemm");
+}
+
+// ---- folded weights of one block ----------------------------------------------------------------
+int fold_block_weights(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int stack_idx,
+                       int kfirst, int nk, const BlockWs& b, cudaStream_t st) {
+  const int W = dm.W, T = dm.multi * dm.W, d = 4 * T;
+  const int PW = (stack_idx == 0) ? T + W : T;
+  for (int c = 0; c < 2; ++c) {
+    SG_TRY(launch_fold_in(bp.glu_left_w[c], b.w1f + (size_t)(c * 2 + 0) * d * nk * W, d, W, c, kfirst, nk, st));
+    SG_TRY(launch_fold_in(bp.glu_right_w[c], b.w1f + (size_t)(c * 2 + 1) * d * nk * W, d, W, c, kfirst, nk, st));
+  }
+  SG_TRY(launch_irfft_table(b.ic, T, st));
+  for (int c = 0; c < 2; ++c) {   // RI[c][k*T+f][u] = sum_t ic[c][f][t] weight[k][t][u]
+    GemmOperands g = {b.ic + (size_t)c * T * T, T, 0, bp.weight, T, (long long)T * T, nullptr, T, T, T};
+    EpiAxpby epi = {b.ri + (size_t)c * 4 * T * T, T, (long long)T * T, nullptr, 0, 0, 1.f, 0.f};
+    SG_TRY((launch_sgemm<false, false, false>(g, epi, 4, st, "fold_out_ri")));
+  }
+  {   // wout[:, 0:T] = RI @ forecast.weight^T ; wout[:, T:T+W] = RI @ backcast.weight^T
+    GemmOperands g = {b.ri, T, 0, bp.forecast_w, T, 0, nullptr, 8 * T, T, T};
+    EpiAxpby epi = {b.wout, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+    SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "fold_out_forecast")));
+    if (stack_idx == 0) {
+      GemmOperands g2 = {b.ri, T, 0, bp.backcast_w, T, 0, nullptr, 8 * T, W, T};
+      EpiAxpby epi2 = {b.wout + T, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+      SG_TRY((launch_sgemm<false, true, false>(g2, epi2, 1, st, "fold_out_backcast")));
+    }
+  }
+  return 0;
+}
+
+// GLU chain on rows G (R x ncol) -> act3 (R x 2d) = [real3 | imag3]
+int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int ncol, int gemm_mode,
+              const BlockWs& b, cudaStream_t st) {
+  const int R = dm.B * dm.N, T = dm.multi * dm.W, d = 4 * T;
+  for (int c = 0; c < 2; ++c) {
+    const float* w1l = b.w1f + (size_t)(c * 2 + 0) * d * ncol;
+    const float* w1r = b.w1f + (size_t)(c * 2 + 1) * d * ncol;
+    float* a1 = b.act1 + (size_t)c * R * d;
+    float* a2 = b.act2 + (size_t)c * R * d;
+    SG_TRY(glu_layer(R, d, ncol, b.G, ncol, w1l, bp.glu_left_b[c], w1r, bp.glu_right_b[c], a1, d,
+                     b.save_l[c], b.save_s[c], gemm_mode, st));
+    SG_TRY(glu_layer(R, d, d, a1, d, bp.glu_left_w[2 + c], bp.glu_left_b[2 + c], bp.glu_right_w[2 + c],
+                     bp.glu_right_b[2 + c], a2, d, b.save_l[2 + c], b.save_s[2 + c], gemm_mode, st));
+    SG_TRY(glu_layer(R, d, d, a2, d, bp.glu_left_w[4 + c], bp.glu_left_b[4 + c], bp.glu_right_w[4 + c],
+                     bp.glu_right_b[4 + c], b.act3 + (size_t)c * d, 2 * d, b.save_l[4 + c],
+                     b.save_s[4 + c], gemm_mode, st));
+  }
+  return 0;
+}
+
+// StockBlockLayer.forward (base_model.py:61-75)
+int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int stack_idx,
+                  int gemm_mode, const float* x_bnw, const float* x_bwn, const float* mul_L,
+                  const BlockWs& b, cudaStream_t st) {
+  const int B = dm.B, N = dm.N, W = dm.W, T = dm.multi * W, d = 4 * T, R = B * N;
+  const int PW = (stack_idx == 0) ? T + W : T;
+  SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
+  SG_TRY(launch_gft(mul_L, x_bwn, b.G, B, N, W, st));
+  SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st));
+  {
+    GemmOperands g = {b.act3, 2 * d, 0, b.wout, PW, 0, nullptr, R, PW, 2 * d};
+    EpiAxpby epi = {b.pre, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+    SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "out_gemm")));
+  }
+  HeadArgs h = {};
+  h.pre = b.pre; h.ldp = PW; h.x_bnw = x_bnw;
+  h.bf = bp.forecast_b; h.wfr = bp.forecast_result_w; h.bfr = bp.forecast_result_b;
+  h.forecast = b.forecast; h.save_fs = b.fs;
+  h.R = R; h.N = N; h.T = T; h.W = W;
+  if (stack_idx == 0) {
+    h.bb = bp.backcast_b; h.wsc = bp.shortcut_w; h.bsc = bp.shortcut_b;
+    h.backcast_bnw = b.bc_bnw; h.backcast_bwn = b.bc_bwn;
+  }
+  return launch_block_head(h, st);
+}
+
+static int check_block_params(const stemgnn_block_params_t* bp, int stack_idx) {
+  SG_CHECK(bp != nullptr, "block params null");
+  SG_CHECK(bp->weight && bp->forecast_w && bp->forecast_b && bp->forecast_result_w &&
+               bp->forecast_result_b, "block %d: null parameter pointer", stack_idx);
+  if (stack_idx == 0)
+    SG_CHECK(bp->backcast_w && bp->backcast_b && bp->shortcut_w && bp->shortcut_b,
+             "block 0: null backcast/shortcut parameter");
+  for (int g = 0; g < 6; ++g)
+    SG_CHECK(bp->glu_left_w[g] && bp->glu_left_b[g] && bp->glu_right_w[g] && bp->glu_right_b[g],
+             "block %d: null GLU %d parameter", stack_idx, g);
+  return 0;
+}
+
+int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const float* key,
+                  const float* query, float* attention, const Workspace& ws, cudaStream_t st) {
+  const int B = dm.B, N = dm.N;
+  AttnArgs a = {};
+  a.key = key; a.query = query; a.qmax = ws.qmax; a.a_raw = ws.a_raw; a.deg = ws.deg;
+  a.row_m = ws.row_m; a.row_zinv = ws.row_zinv;
+  a.mask = op.dropout_mask; a.seed = op.dropout_seed; a.offset = op.dropout_offset;
+  a.alpha = op.leaky_alpha; a.p = op.dropout_p;
+  a.use_dropout = (op.training && (op.dropout_p > 0.f || op.dropout_mask != nullptr)) ? 1 : 0;
+  a.B = B; a.N = N;
+  SG_CHECK(op.dropout_p >= 0.f && op.dropout_p < 1.f, "dropout_p=%f outside [0,1)", op.dropout_p);
+  SG_TRY(launch_attention(a, ws.qmax, st));
+  SG_TRY(launch_laplacian(ws.a_raw, ws.deg, attention, ws.mul_L, N, st));
+  const size_t nn = (size_t)N * N;
+  {   // third = 2 L L   (base_model.py:131; first_laplacian is zero)
+    GemmOperands g = {ws.mul_L + nn, N, 0, ws.mul_L + nn, N, 0, nullptr, N, N, N};
+    EpiAxpby epi = {ws.mul_L + 2 * nn, N, 0, nullptr, 0, 0, 2.f, 0.f};
+    SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb2")));
+  }
+  {   // forth = 2 L third - L   (base_model.py:132)
+    GemmOperands g = {ws.mul_L + nn, N, 0, ws.mul_L + 2 * nn, N, 0, nullptr, N, N, N};
+    EpiAxpby epi = {ws.mul_L + 3 * nn, N, 0, ws.mul_L + nn, N, 0, 2.f, -1.f};
+    SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb3")));
+  }
+  return 0;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int stemgnn_version(void) { return STEMGNN_ABI_VERSION; }
+const char* stemgnn_last_error(void) { return g_err; }
+
+int stemgnn_device_ok(void) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return p.major == 10 ? 1 : 0;
+}
+
+size_t stemgnn_workspace_bytes(const stemgnn_dims_t* dims, int training) {
+  if (dims == nullptr || dims->B <= 0 || dims->N <= 0 || dims->W <= 0 || dims->multi <= 0) return 0;
+  return carve_workspace(*dims, training, nullptr).floats * sizeof(float);
+}
+
+int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
+                          const stemgnn_fwd_opts_t* opts, const float* x, float* forecast,
+                          float* attention, float* mul_L, void* workspace, size_t workspace_bytes,
+                          stemgnn_stream_t stream) {
+  clear_error();
+  SG_TRY(check_dims(dims));
+  SG_CHECK(p && opts && x && forecast && attention, "null argument");
+  SG_CHECK(p->weight_key && p->weight_query && p->gru_w_ih && p->gru_w_hh && p->gru_b_ih &&
+               p->gru_b_hh && p->fc0_w && p->fc0_b && p->fc2_w && p->fc2_b, "null parameter pointer");
+  SG_TRY(check_block_params(&p->block[0], 0));
+  SG_TRY(check_block_params(&p->block[1], 1));
+  SG_TRY(check_ws(dims, opts->training, workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const stemgnn_dims_t& dm = *dims;
+  Workspace ws = carve_workspace(dm, opts->training, static_cast<float*>(workspace));
+
+  SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dm.B, dm.W, dm.N, st));
+  GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
+                p->weight_query, ws.key, ws.query, ws.h_all, dm.B, dm.N, dm.W};
+  SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
+  SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
+  SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, ws.x_bnw, x, ws.mul_L, ws.blk[0], st));
+  SG_TRY(block_forward(dm, p->block[1], 1, opts->gemm_mode, ws.blk[0].bc_bnw, ws.blk[0].bc_bwn,
+                       ws.mul_L, ws.blk[1], st));
+  SG_TRY(launch_model_head(ws.blk[0].forecast, ws.blk[1].forecast, p->fc0_w, p->fc0_b, p->fc2_w,
+                           p->fc2_b, forecast, dm.B, dm.N, dm.W, dm.H, st));
+  if (mul_L != nullptr)
+    SG_CUDA(cudaMemcpyAsync(mul_L, ws.mul_L, (size_t)4 * dm.N * dm.N * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int stemgnn_gru_keyquery_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
+                                 const float* x, float* key, float* query, float* gru_out, int path,
+                                 void* workspace, size_t workspace_bytes, stemgnn_stream_t stream) {
+  clear_error();
+  SG_TRY(check_dims(dims));
+  SG_CHECK(p && x && key && query, "null argument");
+  SG_CHECK(p->weight_key && p->weight_query && p->gru_w_ih && p->gru_w_hh && p->gru_b_ih &&
+               p->gru_b_hh, "null GRU parameter pointer");
+  SG_TRY(check_ws(dims, 0, workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = carve_workspace(*dims, 0, static_cast<float*>(workspace));
+  SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dims->B, dims->W, dims->N, st));
+  GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
+                p->weight_query, key, query, gru_out, dims->B, dims->N, dims->W};
+  return gru_keyquery_forward(ga, path, ws.gru_scratch, st);
+}
+
+int stemgnn_graph_forward(const stemgnn_dims_t* dims, const stemgnn_fwd_opts_t* opts,
+                          const float* key, const float* query, float* attention, float* mul_L,
+                          void* workspace, size_t workspace_bytes, stemgnn_stream_t stream) {
+  clear_error();
+  SG_TRY(check_dims(dims));
+  SG_CHECK(opts && key && query && attention && mul_L, "null argument");
+  stemgnn_fwd_opts_t op = *opts;
+  SG_TRY(check_ws(dims, 0, workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = carve_workspace(*dims, 0, static_cast<float*>(workspace));
+  SG_TRY(graph_forward(*dims, op, key, query, attention, ws, st));
+  SG_CUDA(cudaMemcpyAsync(mul_L, ws.mul_L, (size_t)4 * dims->N * dims->N * sizeof(float),
+                          cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// x_bnw (B,N,W) -> (B,W,N)
+__global__ void bnw_to_bwn_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int N,
+                                  int W) {
+  const long long total = (long long)B * N * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % N), t = (int)((idx / N) % W), b = (int)(idx / ((long long)N * W));
+    out[idx] = in[((long long)b * N + n) * W + t];
+  }
+}
+
+int stemgnn_block_forward(const stemgnn_dims_t* dims, const stemgnn_block_params_t* bp,
+                          int stack_idx, int gemm_mode, const float* x_bnw, const float* mul_L,
+                          float* forecast, float* backcast, void* workspace, size_t workspace_bytes,
+                          stemgnn_stream_t stream) {
+  clear_error();
+  SG_TRY(check_dims(dims));
+  SG_CHECK(stack_idx == 0 || stack_idx == 1, "stack_idx=%d", stack_idx);
+  SG_TRY(check_block_params(bp, stack_idx));
+  SG_CHECK(x_bnw && mul_L && forecast && (stack_idx == 1 || backcast), "null argument");
+  SG_TRY(check_ws(dims, 0, workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = carve_workspace(*dims, 0, static_cast<float*>(workspace));
+  const BlockWs& b = ws.blk[stack_idx];
+  const long long total = (long long)dims->B * dims->N * dims->W;
+  float* x_bwn = ws.blk[1 - stack_idx].bc_bwn;   // scratch from the other block's slot
+  bnw_to_bwn_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x_bnw, x_bwn, dims->B, dims->N, dims->W);
+  SG_LAUNCH_CHECK("bnw_to_bwn_kernel");
+  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, x_bnw, x_bwn, mul_L, b, st));
+  SG_CUDA(cudaMemcpyAsync(forecast, b.forecast, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (stack_idx == 0)
+    SG_CUDA(cudaMemcpyAsync(backcast, b.bc_bnw, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int stemgnn_spe_seq_cell_forward(const stemgnn_dims_t* dims, const stemgnn_block_params_t* bp,
+                                 int gemm_mode, const float* gfted, float* iffted, void* workspace,
+                                 size_t workspace_bytes, stemgnn_stream_t stream) {
+  clear_error();
+  SG_TRY(check_dims(dims));
+  SG_TRY(check_block_params(bp, 1));
+  SG_CHECK(gfted && iffted, "null argument");
+  SG_TRY(check_ws(dims, 0, workspace, workspace_bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = carve_workspace(*dims, 0, static_cast<float*>(workspace));
+  const BlockWs& b = ws.blk[0];
+  const int W = dims->W, T = dims->multi * W;
+  // all four Chebyshev channels are honoured here (a caller may pass a non-zero channel 0)
+  SG_TRY(fold_block_weights(*dims, *bp, 1, 0, 4, b, st));
+  SG_TRY(launch_gfted_to_rows(gfted, b.G, dims->B, dims->N, W, st));
+  SG_TRY(glu_chain(*dims, *bp, 4 * W, gemm_mode, b, st));
+  return launch_irfft_rows(b.act3, b.ic, iffted, dims->B, dims->N, T, st);
+}
+
+int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int a_kmajor,
+                  const float* B, int ldb, int b_nk, float beta, float* C, int ldc,
+                  stemgnn_stream_t stream) {
+  clear_error();
+  SG_CHECK(M >= 0 && N >= 0 && K >= 0 && A && B && C, "sgemm: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmOperands g = {A, lda, 0, B, ldb, 0, nullptr, M, N, K};
+  EpiAxpby epi = {C, ldc, 0, beta != 0.f ? C : nullptr, ldc, 0, alpha, beta};
+  if (!a_kmajor && b_nk) return launch_sgemm<false, true, false>(g, epi, 1, st, "sgemm_nt");
+  if (!a_kmajor && !b_nk) return launch_sgemm<false, false, false>(g, epi, 1, st, "sgemm_nn");
+  if (a_kmajor && b_nk) return launch_sgemm<true, true, false>(g, epi, 1, st, "sgemm_tt");
+  return launch_sgemm<true, false, false>(g, epi, 1, st, "sgemm_tn");
+}
+
+int stemgnn_glu_gemm(int M, int N, int K, const float* A, int lda, const float* Wl, const float* bl,
+                     const float* Wr, const float* br, float* out, int ldo, int use_tc,
+                     stemgnn_stream_t stream) {
+  clear_error();
+  SG_CHECK(M > 0 && N > 0 && K > 0 && A && Wl && bl && Wr && br && out, "glu_gemm: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return glu_layer(M, N, K, A, lda, Wl, bl, Wr, br, out, ldo, nullptr, nullptr, use_tc ? 2 : 1, st);
+}
+
+int stemgnn_model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
+                           const stemgnn_fwd_opts_t* opts, const float* x, const float* d_forecast,
+                           const float* d_attention, const stemgnn_grads_t* grads, float* d_x,
+                           void* workspace, size_t workspace_bytes, stemgnn_stream_t stream) {
+  clear_error();
+  return model_backward(dims, params, opts, x, d_forecast, d_attention, grads, d_x, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

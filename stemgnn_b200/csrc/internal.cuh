@@ -1,0 +1,102 @@
+// Internal (non-ABI) declarations shared by the stemgnn_b200 translation units.
+#pragma once
+#include "common.cuh"
+
+namespace sg {
+
+// ---- GRU (gru.cu) --------------------------------------------------------------------------------
+struct GruArgs {
+  const float* xs;     // (N, B, W) sequence-major input
+  const float* w_ih;   // (3N, W)
+  const float* w_hh;   // (3N, N)
+  const float* b_ih;   // (3N)
+  const float* b_hh;   // (3N)
+  const float* wk;     // (N)  weight_key   (indexed by step)
+  const float* wq;     // (N)  weight_query
+  float* key;          // (B, N)
+  float* query;        // (B, N)
+  float* h_all;        // (N, B, N) or null
+  int B, N, W;
+};
+int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
+
+// ---- attention / Laplacian (latent.cu) ----------------------------------------------------------------
+struct AttnArgs {
+  const float* key;      // (B,N)
+  const float* query;    // (B,N)
+  const float* qmax;     // (B)
+  float* a_raw;          // (N,N) batch mean of (dropped-out) softmax rows, NOT symmetrised
+  float* deg;            // (N)   row sums of a_raw (base_model.py:141)
+  float* row_m;          // (B,N) softmax row max   (saved for backward; may be null)
+  float* row_zinv;       // (B,N) 1 / softmax denominator
+  const uint8_t* mask;   // optional explicit keep mask (B,N,N)
+  uint64_t seed, offset;
+  float alpha, p;
+  int use_dropout;       // 0: eval
+  int B, N;
+};
+int launch_prep_layouts(const float* x, float* xs, float* x_bnw, int B, int W, int N, cudaStream_t st);
+int launch_attention(const AttnArgs& a, float* qmax, cudaStream_t st);
+int launch_laplacian(const float* a_raw, const float* deg, float* attention, float* mul_L, int N,
+                     cudaStream_t st);
+
+// ---- spectral block helpers (spectral.cu) -----------------------------------------------------------
+struct HeadArgs {
+  const float* pre; int ldp;
+  const float* x_bnw;          // (R, W) block input
+  const float* bf; const float* wfr; const float* bfr;
+  const float* bb; const float* wsc; const float* bsc;   // null for block 1
+  float* forecast;             // (R, W)
+  float* backcast_bnw;         // (R, W)    or null
+  float* backcast_bwn;         // (B, W, N) or null
+  float* save_fs;              // (R, T) or null (training)
+  int R, N, T, W;
+};
+int launch_gft(const float* mul_L, const float* x_bwn, float* G, int B, int N, int W, cudaStream_t st);
+int launch_block_head(const HeadArgs& a, cudaStream_t st);
+int launch_model_head(const float* f0, const float* f1, const float* w0, const float* b0,
+                      const float* w2, const float* b2, float* out, int B, int N, int W, int H,
+                      cudaStream_t st);
+int launch_fold_in(const float* w_in, float* w_out, int d, int W, int chain, int kfirst, int nk,
+                   cudaStream_t st);
+int launch_irfft_table(float* ic, int T, cudaStream_t st);
+int launch_irfft_rows(const float* act3, const float* ic, float* iffted, int B, int N, int T,
+                      cudaStream_t st);
+int launch_gfted_to_rows(const float* gfted, float* G4, int B, int N, int W, cudaStream_t st);
+
+// ---- tcgen05 TF32 GLU GEMM (glu_tc.cu): returns 0 ok, -1 unsupported shape/device, >0 error ----------
+int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, const float* bl,
+                const float* Wr, const float* br, float* out, int ldo, float* save_l, float* save_s,
+                int lds, cudaStream_t st);
+
+// ---- workspace ---------------------------------------------------------------------------------------
+struct BlockWs {
+  float* G;        // (R, 3W | 4W) graph-Fourier rows
+  float* w1f;      // [chain][side](d, ncol) DFT-folded first-layer weights
+  float* ic;       // [2](T,T) inverse real DFT table
+  float* ri;       // [2](4T, T) irfft o weight[k]
+  float* wout;     // (8T, T+W) folded output map
+  float* act1;     // [chain](R, d)
+  float* act2;     // [chain](R, d)
+  float* act3;     // (R, 2d) = [real3 | imag3]
+  float* pre;      // (R, T+W)
+  float* forecast; // (R, W)
+  float* bc_bnw;   // (R, W) backcast, block-input layout
+  float* bc_bwn;   // (B, W, N) backcast, GFT operand layout
+  float* save_l[6]; float* save_s[6];   // training: GLU left pre-activation / gate per GLU index
+  float* fs;       // training: forecast_source (R, T)
+};
+struct Workspace {
+  float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch;
+  float *row_m, *row_zinv, *h_all;
+  BlockWs blk[STEMGNN_MAX_STACK];
+  size_t floats;
+};
+Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base);
+
+int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
+                   const stemgnn_fwd_opts_t* opts, const float* x, const float* d_forecast,
+                   const float* d_attention, const stemgnn_grads_t* grads, float* d_x,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+}  // namespace sg
