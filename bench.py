@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — forecast-windows/sec of the StemGNN hot path on B200 (BASELINE.json metric).
+
+A "step" is ONE pass of the hot path (Model.forward in eval(), no_grad — SURVEY.md §8(d)) over one
+batch of synthetic windows at the north-star shape (B,N,W,H)=(32,358,12,3) per GPU (weak scaling:
+every rank owns its own batch; the eval path has no collective).
+
+    python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                      # the reference's CPU path (oracle port)
+
+Prints ONE JSON line.  Keys (see the task contract):
+  value / ms_per_step   device-timed (CUDA events, L2 flushed between steps), inputs resident in HBM
+  e2e                   same metric through the public API with HOST buffers: pinned x -> H2D ->
+                        Model.forward -> D2H of the forecast, all inside the timed region
+  roofline              the dominant kernel (GRU recurrence), timed live with CUDA events via the
+                        library's stemgnn_profile_gru hook; flops = SURVEY.md §8(d) GRU terms
+  cpu_baseline          oracle/torch_port.py (the reference's ATen op sequence) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, N, W, H, MULTI = 32, 358, 12, 3, 5
+WORKLOAD = "synthetic N=358 W=12 H=3 batch=32 fp32 eval forward (BASELINE.json configs[1])"
+METRIC = "forecast-windows/sec (B,N,W)=(32,358,12)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
+    except Exception:
+        return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_forward(steps, warmup):
+    """The reference's CPU path: oracle/torch_port.model_forward (same ATen ops as base_model.py)
+    on all host threads.  Returns (windows_per_s, ms_per_step, threads)."""
+    import torch
+    from oracle import torch_port as tp
+    threads = torch.get_num_threads()
+    p = tp.synthetic_params(N, W, H, MULTI, seed=0)
+    x, _ = tp.synthetic_batch(B, N, W, H)
+    with torch.no_grad():
+        for _ in range(warmup):
+            tp.model_forward(x, p)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tp.model_forward(x, p)
+        dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 40))
+    v, ms, threads = cpu_reference_forward(steps, max(1, min(args.warmup, 3)))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "windows/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "B": B, "N": N, "W": W, "H": H,
+                       "note": "reference CPU path = oracle/torch_port.py (reference's ATen op sequence; "
+                               "the Python reference itself cannot travel to the GPU box)"},
+            "cpu_baseline": {"value": v, "unit": "windows/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} eval forwards of one {B}-window batch; os.cpu_count()={os.cpu_count()}"},
+            "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from models.base_model import Model
+    from oracle import torch_port as tp           # synthetic weights/inputs + cpu_baseline leg only
+    from stemgnn_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+
+    model = Model(N, 2, W, MULTI, horizon=H)
+    model.load_state_dict(tp.synthetic_params(N, W, H, MULTI, seed=0))
+    model = model.to(dev).eval()
+    x_host, _ = tp.synthetic_batch(B, N, W, H, seed=1234 + rank)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            model(x_dev)
+        # ---- device-timed: inputs resident in HBM, L2 flushed between steps -------------------
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        barrier()
+        launches0 = lib.stemgnn_launch_count()
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record()
+            model(x_dev)
+            ev[i][1].record()
+        barrier()
+        launches = lib.stemgnn_launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+        # ---- dominant kernel (GRU recurrence) with CUDA events on the launching stream --------------
+        gru_ms = None
+        try:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); e1.record(); torch.cuda.synchronize()           # materialise the handles
+            tot = 0.0
+            reps = min(args.steps, 10)
+            for _ in range(reps):
+                flush.zero_()
+                lib.stemgnn_profile_gru(e0.cuda_event, e1.cuda_event)
+                model(x_dev)
+                lib.stemgnn_profile_gru(None, None)
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            gru_ms = tot / reps
+        except Exception as exc:                                        # hook is optional evidence
+            gru_ms = None
+            sys.stderr.write(f"[bench] GRU event hook failed: {exc}\n")
+
+        # ---- end to end through the public API with host buffers ----------------------------------
+        out_host = torch.empty(B, H, N).pin_memory()
+        for _ in range(3):
+            f, _a = model(x_host.to(dev, non_blocking=True))
+            out_host.copy_(f, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            xd = x_host.to(dev, non_blocking=True)                      # H2D of the step's input
+            f, _a = model(xd)
+            out_host.copy_(f, non_blocking=True)                        # D2H of the step's result
+            torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    peak_tf, peak_gbs, peak_src = _peaks()
+    gru_flops = 6.0 * B * N ** 3 + 12.0 * B * N * N               # recurrence + gates
+    roof = None
+    if gru_ms:
+        ach = gru_flops / (gru_ms * 1e-3) / 1e12
+        roof = {"kernel": "gru_cluster_kernel (GRU recurrence, fp32 FFMA2, 16-CTA clusters)",
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": gru_ms, "share_of_step": gru_ms / (dev_ms / args.steps),
+                "note": "latency-bound recurrence: 358 dependent steps; flops = 6BN^3 + 12BN^2"}
+    cpu_steps = 15
+    cpu_v, cpu_ms, threads = cpu_reference_forward(cpu_steps, 2)
+    import oracle.stemgnn_oracle as so
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "B_per_gpu": B, "N": N, "W": W, "H": H, "multi_layer": MULTI,
+                       "mode": "eval forward (Model.forward, no_grad)", "parallelism": f"dp{world} replicas",
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+                       "flops_per_step": so.forward_flops(B, N, W, H)},
+            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
+                    "h2d_bytes_per_step": B * W * N * 4, "d2h_bytes_per_step": B * H * N * 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": {"value": cpu_v, "unit": "windows/s", "cores": threads, "kind": "port",
+                             "sample": f"{cpu_steps} eval forwards of one {B}-window batch "
+                                       f"({cpu_ms:.1f} ms each); os.cpu_count()={os.cpu_count()}"},
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

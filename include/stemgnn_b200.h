@@ -108,6 +108,10 @@ typedef struct {
 int stemgnn_version(void);                 /* STEMGNN_ABI_VERSION */
 const char* stemgnn_last_error(void);      /* thread-local, "" if none */
 int stemgnn_device_ok(void);               /* 1 if a usable sm_100 device is current, else 0 */
+long long stemgnn_launch_count(void);      /* kernels launched by this library so far (this process) */
+/* Measurement hook: when both are non-NULL cudaEvent_t, every following forward records them on its
+ * stream immediately before / after the GRU recurrence kernel (the dominant launch); NULL disables. */
+void stemgnn_profile_gru(void* start_event, void* stop_event);
 
 /* Bytes of caller-provided workspace needed by stemgnn_model_forward / _backward for `dims`.
  * The SAME buffer must be passed to the backward of a training forward (it holds the saved

@@ -1,0 +1,185 @@
+"""Train / evaluate driver with the entry points of the reference `models/handler.py`
+(microsoft/StemGNN): `train(train_data, valid_data, args, result_file)`,
+`test(test_data, args, result_train_file, result_test_file)`, `validate(...)`, `inference(...)`,
+`save_model` / `load_model` — so the reference `main.py` runs unchanged against this package
+(`python run_main.py --device cuda:0 ...`).  The model it drives is `models.base_model.Model`,
+whose forward/backward are the stemgnn_b200 CUDA kernels; everything here is host orchestration.
+
+Differences from the reference that are forced by the modern stack:
+`np.float` -> `float`, `torch.load(..., weights_only=False)`.  Behaviour kept on purpose: the
+checkpoint is the whole pickled module, epoch 0 is saved under the "best" name (reference :21),
+LR decays every `exponential_decay_step` epochs, early stopping counts non-improving validations.
+"""
+import json
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.utils.data as torch_data
+
+from data_loader.forecast_dataloader import ForecastDataset, de_normalized
+from models.base_model import Model
+from utils.math_utils import evaluate
+
+_CKPT = '_stemgnn.pt'
+
+
+def _ckpt_path(model_dir, epoch):
+    return os.path.join(model_dir, (str(epoch) if epoch else '') + _CKPT)
+
+
+def save_model(model, model_dir, epoch=None):
+    if model_dir is None:
+        return
+    os.makedirs(model_dir, exist_ok=True)
+    with open(_ckpt_path(model_dir, epoch), 'wb') as f:
+        torch.save(model, f)
+
+
+def load_model(model_dir, epoch=None):
+    if not model_dir:
+        return None
+    os.makedirs(model_dir, exist_ok=True)
+    path = _ckpt_path(model_dir, epoch)
+    if not os.path.exists(path):
+        return None
+    with open(path, 'rb') as f:
+        return torch.load(f, weights_only=False)
+
+
+def inference(model, dataloader, device, node_cnt, window_size, horizon):
+    """Rolling forecast: the model emits `len_out` steps per call; the window is shifted by the
+    prediction until `horizon` steps exist (one call per batch when the model emits the full
+    horizon).  Returns (forecast, target) numpy arrays of shape (count, horizon, node)."""
+    forecasts, targets = [], []
+    model.eval()
+    with torch.no_grad():
+        for inputs, target in dataloader:
+            inputs, target = inputs.to(device), target.to(device)
+            steps = np.zeros([inputs.size(0), horizon, node_cnt], dtype=float)
+            done = 0
+            while done < horizon:
+                out, _ = model(inputs)
+                len_out = out.size(1)
+                if len_out == 0:
+                    raise Exception('Get blank inference result')
+                inputs[:, :window_size - len_out, :] = inputs[:, len_out:window_size, :].clone()
+                inputs[:, window_size - len_out:, :] = out.clone()
+                take = min(horizon - done, len_out)
+                steps[:, done:done + take, :] = out[:, :take, :].detach().cpu().numpy()
+                done += take
+            forecasts.append(steps)
+            targets.append(target.detach().cpu().numpy())
+    return np.concatenate(forecasts, axis=0), np.concatenate(targets, axis=0)
+
+
+def validate(model, dataloader, device, normalize_method, statistic, node_cnt, window_size, horizon,
+             result_file=None):
+    forecast_norm, target_norm = inference(model, dataloader, device, node_cnt, window_size, horizon)
+    if normalize_method and statistic:
+        forecast = de_normalized(forecast_norm, normalize_method, statistic)
+        target = de_normalized(target_norm, normalize_method, statistic)
+    else:
+        forecast, target = forecast_norm, target_norm
+    score = evaluate(target, forecast)
+    score_by_node = evaluate(target, forecast, by_node=True)
+    score_norm = evaluate(target_norm, forecast_norm)
+    print(f'NORM: MAPE {score_norm[0]:7.9%}; MAE {score_norm[1]:7.9f}; RMSE {score_norm[2]:7.9f}.')
+    print(f'RAW : MAPE {score[0]:7.9%}; MAE {score[1]:7.9f}; RMSE {score[2]:7.9f}.')
+    if result_file:
+        os.makedirs(result_file, exist_ok=True)
+        pred, truth = forecast[:, 0, :], target[:, 0, :]
+        np.savetxt(f'{result_file}/target.csv', truth, delimiter=",")
+        np.savetxt(f'{result_file}/predict.csv', pred, delimiter=",")
+        np.savetxt(f'{result_file}/predict_abs_error.csv', np.abs(pred - truth), delimiter=",")
+        np.savetxt(f'{result_file}/predict_ape.csv', np.abs((pred - truth) / truth), delimiter=",")
+    return dict(mae=score[1], mae_node=score_by_node[1], mape=score[0], mape_node=score_by_node[0],
+                rmse=score[2], rmse_node=score_by_node[2])
+
+
+def _norm_statistic(train_data, method):
+    if method == 'z_score':
+        return {"mean": np.mean(train_data, axis=0).tolist(), "std": np.std(train_data, axis=0).tolist()}
+    if method == 'min_max':
+        return {"min": np.min(train_data, axis=0).tolist(), "max": np.max(train_data, axis=0).tolist()}
+    return None
+
+
+def train(train_data, valid_data, args, result_file):
+    node_cnt = train_data.shape[1]
+    model = Model(node_cnt, 2, args.window_size, args.multi_layer, horizon=args.horizon)
+    model.to(args.device)
+    if len(train_data) == 0:
+        raise Exception('Cannot organize enough training data')
+    if len(valid_data) == 0:
+        raise Exception('Cannot organize enough validation data')
+
+    normalize_statistic = _norm_statistic(train_data, args.norm_method)
+    if normalize_statistic is not None:
+        with open(os.path.join(result_file, 'norm_stat.json'), 'w') as f:
+            json.dump(normalize_statistic, f)
+
+    if args.optimizer == 'RMSProp':
+        optim = torch.optim.RMSprop(params=model.parameters(), lr=args.lr, eps=1e-08)
+    else:
+        optim = torch.optim.Adam(params=model.parameters(), lr=args.lr, betas=(0.9, 0.999))
+    scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer=optim, gamma=args.decay_rate)
+
+    ds_kw = dict(window_size=args.window_size, horizon=args.horizon, normalize_method=args.norm_method,
+                 norm_statistic=normalize_statistic)
+    train_loader = torch_data.DataLoader(ForecastDataset(train_data, **ds_kw), batch_size=args.batch_size,
+                                         drop_last=False, shuffle=True, num_workers=0)
+    valid_loader = torch_data.DataLoader(ForecastDataset(valid_data, **ds_kw), batch_size=args.batch_size,
+                                         shuffle=False, num_workers=0)
+    criterion = nn.MSELoss(reduction='mean').to(args.device)
+    print(f"Total Trainable Params: {sum(p.numel() for p in model.parameters() if p.requires_grad)}")
+
+    best_mae, stale, metrics = np.inf, 0, {}
+    for epoch in range(args.epoch):
+        t0 = time.time()
+        model.train()
+        loss_total, cnt = 0.0, 0
+        for inputs, target in train_loader:
+            inputs, target = inputs.to(args.device), target.to(args.device)
+            model.zero_grad()
+            forecast, _ = model(inputs)
+            loss = criterion(forecast, target)
+            cnt += 1
+            loss.backward()
+            optim.step()
+            loss_total += float(loss)
+        print('| end of epoch {:3d} | time: {:5.2f}s | train_total_loss {:5.4f}'.format(
+            epoch, time.time() - t0, loss_total / cnt))
+        save_model(model, result_file, epoch)
+        if (epoch + 1) % args.exponential_decay_step == 0:
+            scheduler.step()
+        if (epoch + 1) % args.validate_freq == 0:
+            print('------ validate on data: VALIDATE ------')
+            metrics = validate(model, valid_loader, args.device, args.norm_method, normalize_statistic,
+                               node_cnt, args.window_size, args.horizon, result_file=result_file)
+            if best_mae > metrics['mae']:
+                best_mae, stale = metrics['mae'], 0
+                save_model(model, result_file)
+            else:
+                stale += 1
+        if args.early_stop and stale >= args.early_stop_step:
+            break
+    return metrics, normalize_statistic
+
+
+def test(test_data, args, result_train_file, result_test_file):
+    with open(os.path.join(result_train_file, 'norm_stat.json'), 'r') as f:
+        normalize_statistic = json.load(f)
+    model = load_model(result_train_file)
+    node_cnt = test_data.shape[1]
+    test_set = ForecastDataset(test_data, window_size=args.window_size, horizon=args.horizon,
+                               normalize_method=args.norm_method, norm_statistic=normalize_statistic)
+    test_loader = torch_data.DataLoader(test_set, batch_size=args.batch_size, drop_last=False,
+                                        shuffle=False, num_workers=0)
+    m = validate(model, test_loader, args.device, args.norm_method, normalize_statistic, node_cnt,
+                 args.window_size, args.horizon, result_file=result_test_file)
+    print('Performance on test set: MAPE: {:5.2f} | MAE: {:5.2f} | RMSE: {:5.4f}'.format(
+        m['mape'], m['mae'], m['rmse']))

@@ -17,6 +17,11 @@ void set_error(const char* fmt, ...) {
 }
 void clear_error() { g_err[0] = 0; }
 
+static long long g_launches = 0;           // one host thread drives one device (process per GPU)
+void count_launch() { ++g_launches; }
+static ProfileHook g_hook = {nullptr, nullptr};
+ProfileHook* profile_hook() { return &g_hook; }
+
 // ---- workspace layout (offsets in floats, 256-byte aligned) -------------------------------------
 Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
   Workspace ws = {};
@@ -37,6 +42,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
   ws.mul_L = take(4 * N * N);
   ws.attention = take(N * N);
   ws.gru_scratch = take(2 * R);
+  ws.gi = take(N * R * 3);
   ws.row_m = training ? take(R) : nullptr;
   ws.row_zinv = training ? take(R) : nullptr;
   ws.h_all = training ? take(N * R) : nullptr;
@@ -219,6 +225,13 @@ extern "C" {
 int stemgnn_version(void) { return STEMGNN_ABI_VERSION; }
 const char* stemgnn_last_error(void) { return g_err; }
 
+long long stemgnn_launch_count(void) { return g_launches; }
+
+void stemgnn_profile_gru(void* start_event, void* stop_event) {
+  g_hook.start = static_cast<cudaEvent_t>(start_event);
+  g_hook.stop = static_cast<cudaEvent_t>(stop_event);
+}
+
 int stemgnn_device_ok(void) {
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
@@ -250,7 +263,7 @@ int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
 
   SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dm.B, dm.W, dm.N, st));
   GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
-                p->weight_query, ws.key, ws.query, ws.h_all, dm.B, dm.N, dm.W};
+                p->weight_query, ws.key, ws.query, ws.h_all, ws.gi, dm.B, dm.N, dm.W};
   SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
   SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
   SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, ws.x_bnw, x, ws.mul_L, ws.blk[0], st));
@@ -277,7 +290,7 @@ int stemgnn_gru_keyquery_forward(const stemgnn_dims_t* dims, const stemgnn_param
   Workspace ws = carve_workspace(*dims, 0, static_cast<float*>(workspace));
   SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dims->B, dims->W, dims->N, st));
   GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
-                p->weight_query, key, query, gru_out, dims->B, dims->N, dims->W};
+                p->weight_query, key, query, gru_out, ws.gi, dims->B, dims->N, dims->W};
   return gru_keyquery_forward(ga, path, ws.gru_scratch, st);
 }
 

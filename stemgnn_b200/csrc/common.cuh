@@ -12,6 +12,10 @@ namespace sg {
 // ---- error plumbing: C ABI returns int, message is thread-local -------------------------
 void set_error(const char* fmt, ...);
 void clear_error();
+void count_launch();                       // bumps the counter behind stemgnn_launch_count()
+// optional event pair recorded around the GRU recurrence kernel (stemgnn_profile_gru)
+struct ProfileHook { cudaEvent_t start, stop; };
+ProfileHook* profile_hook();
 
 #define SG_CHECK(cond, ...)                      \
   do {                                           \
@@ -38,6 +42,7 @@ void clear_error();
       sg::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));       \
       return 3;                                                                     \
     }                                                                               \
+    sg::count_launch();                                                             \
   } while (0)
 
 #define SG_TRY(expr)            \

@@ -9,14 +9,15 @@
 //     shared memory for all N steps (persistent-RNN), so W_hh is read from HBM exactly once;
 //   * per step: packed-fp32 (FFMA2) mat-vec against the 4 hidden vectors, gate math, then the new
 //     hidden slice is scattered into every CTA's next-step buffer through DISTRIBUTED SHARED
-//     MEMORY and one cluster barrier (arrive / wait split; the input projection W_ih x_{s+1} of
-//     the next step is computed between arrive and wait);
+//     MEMORY and one cluster barrier; the input projection W_ih x_s + b_ih of all steps is one
+//     parallel GEMM beforehand (gru_input_proj) whose rows are prefetched a step ahead;
 //   * key/query (sum over steps of h_s * w[s]) are accumulated in registers, so the (N,B,N) GRU
 //     output is never materialised in eval mode (it is written only when the backward needs it).
 // A generic per-step-launch path covers N > 512 or devices that refuse the 16-CTA cluster.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "gemm.cuh"
 #include "internal.cuh"
 
 namespace cg = cooperative_groups;
@@ -24,7 +25,6 @@ namespace cg = cooperative_groups;
 namespace sg {
 
 
-constexpr int GRU_BC = 4;        // batch elements per cluster
 constexpr int GRU_WARPS = 8;
 constexpr int GRU_THREADS = GRU_WARPS * 32;
 
@@ -35,28 +35,82 @@ __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
-// JC: K padded to 128*JC;  UPW: hidden units per warp;  CS: cluster size
-template <int JC, int UPW, int CS>
+// Warp-wide sum of C values per lane (C a power of two <= 32) by recursive halving: after log2(C)
+// exchange stages every lane owns ONE column sum; lane l ends with the total of value l / (32/C).
+// Costs C-1 + (5 - log2 C) shuffles instead of 5*C.
+template <int C>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[C], int lane) {
+  if constexpr (C == 1) {
+    float r = v[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+  } else {
+    constexpr int LOG = (C == 32) ? 5 : (C == 16) ? 4 : (C == 8) ? 3 : (C == 4) ? 2 : 1;
+    int o = 16;
+    int n = C;
+#pragma unroll
+    for (int st = 0; st < LOG; ++st) {
+      const int half = n >> 1;
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < C / 2; ++i) {
+        if (i < half) {
+          const float send = up ? v[i] : v[i + half];
+          const float keep = up ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      n = half;
+      o >>= 1;
+    }
+    float r = v[0];
+#pragma unroll
+    for (int st = LOG; st < 5; ++st) {
+      r += __shfl_xor_sync(0xffffffffu, r, o);
+      o >>= 1;
+    }
+    return r;
+  }
+}
+
+// reduce V = sum of power-of-two chunks; writes the V totals to out[0..V) (one lane per value)
+template <int V, int OFF = 0>
+__device__ __forceinline__ void warp_reduce_to_smem(const float* vals, float* out, int lane) {
+  if constexpr (V > 0) {
+    constexpr int C = (V >= 32) ? 32 : (V >= 16) ? 16 : (V >= 8) ? 8 : (V >= 4) ? 4 : (V >= 2) ? 2 : 1;
+    float v[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) v[i] = vals[OFF + i];
+    const float r = warp_reduce_scatter<C>(v, lane);
+    if ((lane % (32 / C)) == 0) out[OFF + lane / (32 / C)] = r;
+    warp_reduce_to_smem<V - C, OFF + C>(vals, out, lane);
+  }
+}
+
+// JC: K padded to 128*JC;  UPW: hidden units per warp;  CS: cluster size;  BC: sequences per cluster
+template <int JC, int UPW, int CS, int BC>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) {
   constexpr int KP = 128 * JC;
-  constexpr int NJ = KP / 32;               // float4 chunks per lane
   constexpr int ULOC = GRU_WARPS * UPW;     // padded units per CTA
-  constexpr int ROWS = 3 * UPW;             // rows per warp
+  constexpr int ROWS = 3 * UPW;             // W_hh rows per warp
+  constexpr int V = ROWS * BC;              // dot products per warp per step
+  static_assert(UPW * BC <= 32, "finalising lanes");
 
   extern __shared__ __align__(16) float smem[];
   float* Wsm = smem;                              // [3*ULOC][KP]
   float* hbuf = Wsm + 3 * ULOC * KP;              // [2][BC][KP]
-  float* stage = hbuf + 2 * GRU_BC * KP;          // [BC][32]
+  float* stage = hbuf + 2 * BC * KP;              // [BC][32]
+  float* sums = stage + BC * 32;                  // [WARPS][V]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
   const int cid = blockIdx.x / CS;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int b = lane >> 3, kg = lane & 7;
-  const int N = a.N, B = a.B, W = a.W;
+  const int N = a.N, B = a.B;
   const int U = (N + CS - 1) / CS;
   const int u0 = q * U;
-  const int b0 = cid * GRU_BC;
+  const int b0 = cid * BC;
 
   // ---- one-time: W_hh slice -> smem (zero padded), h buffers = 0 ---------------------------
   for (int idx = tid; idx < 3 * ULOC * KP; idx += GRU_THREADS) {
@@ -67,13 +121,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
     if (lu < U && u < N && k < N) v = __ldg(a.w_hh + ((long long)gate * N + u) * N + k);
     Wsm[idx] = v;
   }
-  for (int idx = tid; idx < 2 * GRU_BC * KP; idx += GRU_THREADS) hbuf[idx] = 0.f;
+  for (int idx = tid; idx < 2 * BC * KP; idx += GRU_THREADS) hbuf[idx] = 0.f;
 
-  // finalising lanes: lane (b, kg) with kg < UPW owns local unit lu = w*UPW + kg for batch b
-  const int lu = w * UPW + kg;
+  // finalising lanes: lane t < UPW*BC owns (local unit w*UPW + t/BC, sequence t%BC)
+  const int fi = lane / BC, fb = lane - fi * BC;
+  const int lu = w * UPW + fi;
   const int u = u0 + lu;
-  const bool fin = (kg < UPW) && (lu < U) && (u < N);
-  const bool bvalid = (b0 + b) < B;
+  const bool flane = lane < UPW * BC;
+  const bool fin = flane && (lu < U) && (u < N);
+  const bool bvalid = (b0 + fb) < B;
   float bhr = 0.f, bhz = 0.f, bhn = 0.f;
   if (fin) {
     bhr = __ldg(a.b_hh + u);
@@ -82,30 +138,19 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
   }
   float key_acc = 0.f, query_acc = 0.f;
 
-  // input projection of step s for this lane's (unit, batch): W_i{r,z,n} x_s + b_i{r,z,n}
-  auto input_proj = [&](int s, float& gr, float& gz, float& gn) {
+  // input projection W_i{r,z,n} x_s + b_i{r,z,n} comes precomputed (gru_input_proj); the values of
+  // step s+1 are requested at the top of step s so their latency hides behind the mat-vec.
+  auto load_gi = [&](int s, float& gr, float& gz, float& gn) {
     gr = gz = gn = 0.f;
-    if (fin) {
-      gr = __ldg(a.b_ih + u);
-      gz = __ldg(a.b_ih + N + u);
-      gn = __ldg(a.b_ih + 2 * N + u);
-      if (bvalid) {
-        const float* xrow = a.xs + ((long long)s * B + (b0 + b)) * W;
-        const float* wr = a.w_ih + (long long)u * W;
-        const float* wz = a.w_ih + (long long)(N + u) * W;
-        const float* wn = a.w_ih + (long long)(2 * N + u) * W;
-        for (int t = 0; t < W; ++t) {
-          const float xv = __ldg(xrow + t);
-          gr = fmaf(__ldg(wr + t), xv, gr);
-          gz = fmaf(__ldg(wz + t), xv, gz);
-          gn = fmaf(__ldg(wn + t), xv, gn);
-        }
-      }
+    if (fin && bvalid) {
+      const float* g = a.gi + ((long long)s * B + (b0 + fb)) * (3 * N) + u;
+      gr = __ldg(g);
+      gz = __ldg(g + N);
+      gn = __ldg(g + 2 * N);
     }
   };
-
   float gi_r, gi_z, gi_n;
-  input_proj(0, gi_r, gi_z, gi_n);
+  load_gi(0, gi_r, gi_z, gi_n);
   float wk_s = __ldg(a.wk + 0), wq_s = __ldg(a.wq + 0);
 
   __syncthreads();
@@ -113,50 +158,55 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
 
   for (int s = 0; s < N; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
-    // (a) this lane's slice of h_{s-1} for batch b: k = 32*jj + 4*kg + {0..3}
-    const float* hb = hbuf + (cur * GRU_BC + b) * KP + 4 * kg;
-    float4 h[NJ];
+    float nx_r = 0.f, nx_z = 0.f, nx_n = 0.f, nx_wk = 0.f, nx_wq = 0.f;
+    if (s + 1 < N) {
+      load_gi(s + 1, nx_r, nx_z, nx_n);
+      nx_wk = __ldg(a.wk + s + 1);
+      nx_wq = __ldg(a.wq + s + 1);
+    }
+    // (a) this lane's k-slice of h_{s-1} for all BC sequences: k = 128*j + 4*lane + {0..3}
+    float4 h[BC][JC];
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) h[jj] = *reinterpret_cast<const float4*>(hb + 32 * jj);
+    for (int bb = 0; bb < BC; ++bb)
+#pragma unroll
+      for (int j = 0; j < JC; ++j)
+        h[bb][j] = *reinterpret_cast<const float4*>(hbuf + (cur * BC + bb) * KP + 128 * j + 4 * lane);
 
-    // (b) mat-vec: ROWS rows of this warp against the lane's k-slice (two partial sums / row)
-    float2 acc[ROWS];
-    const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * kg;
+    // (b) mat-vec: each W_hh element is read from shared memory exactly once per step (32 lanes x 16 B
+    //     distinct per LDS.128) and used for all BC sequences; two partial sums per (row, sequence).
+    float2 acc[ROWS][BC];
+    const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * lane;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      acc[r] = make_float2(0.f, 0.f);
-      const float* wrow = wbase + r * KP;
 #pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) {
-        const float4 wv = *reinterpret_cast<const float4*>(wrow + 32 * jj);
-        acc[r] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[jj].x, h[jj].y), acc[r]);
-        acc[r] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[jj].z, h[jj].w), acc[r]);
+      for (int bb = 0; bb < BC; ++bb) acc[r][bb] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < JC; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(wbase + r * KP + 128 * j);
+#pragma unroll
+        for (int bb = 0; bb < BC; ++bb) {
+          acc[r][bb] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[bb][j].x, h[bb][j].y), acc[r][bb]);
+          acc[r][bb] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[bb][j].z, h[bb][j].w), acc[r][bb]);
+        }
       }
     }
-    // (c) reduce over the 8 k-groups (lanes sharing b)
-    float sum[ROWS];
+    // (c) reduce the V partial dot products over the 32 lanes (recursive halving) -> sums[w][V]
+    float part[V];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      float v = acc[r].x + acc[r].y;
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      sum[r] = v;
-    }
-    // (d) gates for (unit lu, batch b) on lanes kg < UPW
-    float gh_r = 0.f, gh_z = 0.f, gh_n = 0.f;
+    for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-    for (int i = 0; i < UPW; ++i) {
-      if (kg == i) {
-        gh_r = sum[3 * i];
-        gh_z = sum[3 * i + 1];
-        gh_n = sum[3 * i + 2];
-      }
-    }
-    if (kg < UPW) {
+      for (int bb = 0; bb < BC; ++bb) part[r * BC + bb] = acc[r][bb].x + acc[r][bb].y;
+    float* wsum = sums + w * V;
+    warp_reduce_to_smem<V>(part, wsum, lane);
+    __syncwarp();
+    // (d) gates for (unit, sequence) on the first UPW*BC lanes
+    if (flane) {
       float hn = 0.f;
       if (fin) {
-        const float hprev = hbuf[(cur * GRU_BC + b) * KP + u];
+        const float gh_r = wsum[(3 * fi + 0) * BC + fb];
+        const float gh_z = wsum[(3 * fi + 1) * BC + fb];
+        const float gh_n = wsum[(3 * fi + 2) * BC + fb];
+        const float hprev = hbuf[(cur * BC + fb) * KP + u];
         const float r = sigmoidf_(gi_r + gh_r + bhr);
         const float zt = sigmoidf_(gi_z + gh_z + bhz);
         const float nt = tanhf(gi_n + r * (gh_n + bhn));
@@ -164,7 +214,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
         key_acc = fmaf(hn, wk_s, key_acc);
         query_acc = fmaf(hn, wq_s, query_acc);
       }
-      stage[b * 32 + lu] = hn;
+      stage[fb * 32 + lu] = hn;
     }
     __syncthreads();
     // (e) scatter the CTA's new slice into every cluster CTA's next buffer (DSMEM)
@@ -173,44 +223,36 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
       for (int d = w; d < CS; d += GRU_WARPS) {
         float* remote = cluster.map_shared_rank(hbuf, d);
 #pragma unroll
-        for (int bb = 0; bb < GRU_BC; ++bb)
-          remote[(nxt * GRU_BC + bb) * KP + u0 + lane] = stage[bb * 32 + lane];
+        for (int bb = 0; bb < BC; ++bb)
+          remote[(nxt * BC + bb) * KP + u0 + lane] = stage[bb * 32 + lane];
       }
     }
-    if (a.h_all != nullptr && w < GRU_BC && (b0 + w) < B && lane < U && (u0 + lane) < N)
+    if (a.h_all != nullptr && w < BC && (b0 + w) < B && lane < U && (u0 + lane) < N)
       a.h_all[((long long)s * B + (b0 + w)) * N + u0 + lane] = stage[w * 32 + lane];
-    // (f) barrier; overlap the next step's input projection with the wait
+    // (f) one cluster barrier per step: all slices of h_s are visible before step s+1 reads them
     __syncwarp();
     cluster_arrive_release();
-    if (s + 1 < N) {
-      input_proj(s + 1, gi_r, gi_z, gi_n);
-      wk_s = __ldg(a.wk + s + 1);
-      wq_s = __ldg(a.wq + s + 1);
-    }
-    __syncwarp();
+    gi_r = nx_r; gi_z = nx_z; gi_n = nx_n; wk_s = nx_wk; wq_s = nx_wq;
     cluster_wait_acquire();
   }
 
   if (fin && bvalid) {
-    a.key[(long long)(b0 + b) * N + u] = key_acc;
-    a.query[(long long)(b0 + b) * N + u] = query_acc;
+    a.key[(long long)(b0 + fb) * N + u] = key_acc;
+    a.query[(long long)(b0 + fb) * N + u] = query_acc;
   }
 }
 
-template <int JC, int UPW, int CS>
-static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, bool probe_only) {
+// returns 0 launched, -1 configuration not launchable here, >0 error
+template <int JC, int UPW, int CS, int BC>
+static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, int* max_active_out) {
   constexpr int KP = 128 * JC;
   constexpr int ULOC = GRU_WARPS * UPW;
-  const size_t smem = (size_t)(3 * ULOC * KP + 2 * GRU_BC * KP + GRU_BC * 32) * sizeof(float);
-  auto kern = gru_cluster_kernel<JC, UPW, CS>;
+  const size_t smem =
+      (size_t)(3 * ULOC * KP + 2 * BC * KP + BC * 32 + GRU_WARPS * 3 * UPW * BC) * sizeof(float);
+  auto kern = gru_cluster_kernel<JC, UPW, CS, BC>;
   static bool attr_set = false;   // one process drives one device (DDP = process per GPU)
-  if (!attr_set) {
-    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CS > 8)
-      SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
-  }
-  const int nclusters = ceil_div(a.B, GRU_BC);
+  static int max_clusters = 0;
+  const int nclusters = ceil_div(a.B, BC);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
   cfg.blockDim = dim3(GRU_THREADS);
@@ -223,25 +265,37 @@ static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, bool probe_only
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int max_clusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-  if (e != cudaSuccess || max_clusters < 1) {
-    (void)cudaGetLastError();
-    return -1;   // not launchable with this cluster size on this device
+  if (!attr_set) {
+    if (smem > 227 * 1024) return -1;
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8)
+      SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      max_clusters = 0;
+    }
+    attr_set = true;
   }
-  if (probe_only) return 0;
+  if (max_active_out != nullptr) *max_active_out = max_clusters;
+  if (max_clusters < 1) return -1;
+  if (max_active_out != nullptr) return 0;      // probe only
+  ProfileHook* hook = profile_hook();
+  if (hook->start != nullptr) SG_CUDA(cudaEventRecord(hook->start, st));
   SG_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  if (hook->stop != nullptr) SG_CUDA(cudaEventRecord(hook->stop, st));
+  count_launch();
   return 0;
 }
 
-template <int CS>
-static int dispatch_gru_cluster(const GruArgs& a, cudaStream_t st) {
+template <int CS, int BC>
+static int dispatch_gru_cluster(const GruArgs& a, cudaStream_t st, int* probe) {
   const int U = ceil_div(a.N, CS);
   const int upw = ceil_div(U, GRU_WARPS);
   const int jc = ceil_div(a.N, 128);
   if (upw > 4 || jc > 4) return -1;
 #define SG_GRU_CASE(J, P) \
-  if (jc == J && upw == P) return launch_gru_cluster<J, P, CS>(a, st, false);
+  if (jc == J && upw == P) return launch_gru_cluster<J, P, CS, BC>(a, st, probe);
   SG_GRU_CASE(1, 1) SG_GRU_CASE(1, 2) SG_GRU_CASE(1, 3) SG_GRU_CASE(1, 4)
   SG_GRU_CASE(2, 1) SG_GRU_CASE(2, 2) SG_GRU_CASE(2, 3) SG_GRU_CASE(2, 4)
   SG_GRU_CASE(3, 1) SG_GRU_CASE(3, 2) SG_GRU_CASE(3, 3) SG_GRU_CASE(3, 4)
@@ -256,7 +310,7 @@ __global__ void __launch_bounds__(128) gru_step_kernel(GruArgs a, int s, const f
                                                        float* __restrict__ h_next) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int u = blockIdx.x * 4 + wid;
-  const int N = a.N, B = a.B, W = a.W;
+  const int N = a.N, B = a.B;
   if (u >= N) return;
   const float* wr = a.w_hh + (long long)u * N;
   const float* wz = a.w_hh + (long long)(N + u) * N;
@@ -288,14 +342,8 @@ __global__ void __launch_bounds__(128) gru_step_kernel(GruArgs a, int s, const f
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (lane == j) { gh_r = acc[0][j]; gh_z = acc[1][j]; gh_n = acc[2][j]; }
-      float gr = __ldg(a.b_ih + u), gz = __ldg(a.b_ih + N + u), gn = __ldg(a.b_ih + 2 * N + u);
-      const float* xrow = a.xs + ((long long)s * B + bi) * W;
-      for (int t = 0; t < W; ++t) {
-        const float xv = __ldg(xrow + t);
-        gr = fmaf(__ldg(a.w_ih + (long long)u * W + t), xv, gr);
-        gz = fmaf(__ldg(a.w_ih + (long long)(N + u) * W + t), xv, gz);
-        gn = fmaf(__ldg(a.w_ih + (long long)(2 * N + u) * W + t), xv, gn);
-      }
+      const float* gp = a.gi + ((long long)s * B + bi) * (3 * N) + u;
+      const float gr = __ldg(gp), gz = __ldg(gp + N), gn = __ldg(gp + 2 * N);
       const float r = sigmoidf_(gr + gh_r + __ldg(a.b_hh + u));
       const float zt = sigmoidf_(gz + gh_z + __ldg(a.b_hh + N + u));
       const float nt = tanhf(gn + r * (gh_n + __ldg(a.b_hh + 2 * N + u)));
@@ -309,15 +357,37 @@ __global__ void __launch_bounds__(128) gru_step_kernel(GruArgs a, int s, const f
   }
 }
 
+// gi[(s*B+b)][g*N+u] = W_i{g} x_s[b] + b_i{g}   for all steps at once: (N*B x W) . (W x 3N)
+int gru_input_proj(const GruArgs& a, cudaStream_t st) {
+  GemmOperands g = {a.xs, a.W, 0, a.w_ih, a.W, 0, nullptr, a.N * a.B, 3 * a.N, a.W};
+  EpiBias<0> epi = {a.gi, 3 * a.N, 0, a.b_ih, 0};
+  return launch_sgemm<false, true, false>(g, epi, 1, st, "gru_input_proj");
+}
+
 // scratch: 2*B*N floats (ping-pong hidden state) for the generic path
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st) {
   SG_CHECK(a.B > 0 && a.N > 0 && a.W > 0, "gru: bad dims B=%d N=%d W=%d", a.B, a.N, a.W);
+  SG_TRY(gru_input_proj(a, st));
   if (path != 1) {
-    int rc = dispatch_gru_cluster<16>(a, st);
-    if (rc == 0) return 0;
-    if (rc > 0) return rc;
+    // 16-CTA clusters, 4 sequences each; if the device cannot keep ceil(B/4) clusters resident at
+    // once (B200: 7 clusters of 16) but can with 5 sequences per cluster, use 5 and stay in one wave.
+    int max_active = 0;
+    int rc = dispatch_gru_cluster<16, 4>(a, st, &max_active);
+    if (rc == 0) {
+      const int need4 = ceil_div(a.B, 4), need5 = ceil_div(a.B, 5);
+      if (need4 > max_active && need5 <= max_active && need4 <= 2 * max_active) {
+        rc = dispatch_gru_cluster<16, 5>(a, st, nullptr);
+        if (rc == 0) return 0;
+        if (rc > 0) return rc;
+      }
+      rc = dispatch_gru_cluster<16, 4>(a, st, nullptr);
+      if (rc == 0) return 0;
+      if (rc > 0) return rc;
+    } else if (rc > 0) {
+      return rc;
+    }
     if (a.N <= 256) {
-      rc = dispatch_gru_cluster<8>(a, st);
+      rc = dispatch_gru_cluster<8, 4>(a, st, nullptr);
       if (rc == 0) return 0;
       if (rc > 0) return rc;
     }
@@ -331,6 +401,7 @@ int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_
     const float* hp = scratch + (size_t)(s & 1) * bn;
     float* hn = scratch + (size_t)((s & 1) ^ 1) * bn;
     gru_step_kernel<<<ceil_div(a.N, 4), 128, 0, st>>>(a, s, hp, hn);
+    count_launch();
   }
   SG_LAUNCH_CHECK("gru_step_kernel");
   return 0;

@@ -16,6 +16,7 @@ struct GruArgs {
   float* key;          // (B, N)
   float* query;        // (B, N)
   float* h_all;        // (N, B, N) or null
+  float* gi;           // (N, B, 3N) scratch: input projection of every step
   int B, N, W;
 };
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
@@ -87,7 +88,7 @@ struct BlockWs {
   float* fs;       // training: forecast_source (R, T)
 };
 struct Workspace {
-  float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch;
+  float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
   float *row_m, *row_zinv, *h_all;
   BlockWs blk[STEMGNN_MAX_STACK];
   size_t floats;

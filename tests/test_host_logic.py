@@ -1,0 +1,202 @@
+"""CPU tests of the host-side mirror of the reference interface (handler / dataloader / metrics) and
+of the C-ABI surface.  Where /root/reference is mounted (build container) the reference's own
+functions are imported through oracle/ref_shim.py and compared on identical inputs."""
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+def _ref(modname):
+    with ref_shim.reference_modules():
+        return importlib.import_module(modname)
+
+
+# ---- metrics ------------------------------------------------------------------------------------
+def test_metrics_known_values():
+    from utils.math_utils import MAE, MAPE, RMSE, evaluate
+    y = np.array([[[1.0, 2.0], [4.0, -2.0]]])
+    p = np.array([[[2.0, 2.0], [2.0, 20.0]]])
+    assert MAE(y, p) == pytest.approx((1 + 0 + 2 + 22) / 4)
+    assert RMSE(y, p) == pytest.approx(np.sqrt((1 + 0 + 4 + 484) / 4))
+    assert MAPE(y, p) == pytest.approx((1 + 1e-5 + 1e-5 + 0.5 + 1e-5 + 5.0) / 4)   # last term clipped at 5
+    m = evaluate(y, p, by_node=True)
+    assert m[1].shape == (2,)
+    assert evaluate(y, p, by_step=True)[2].shape == (2,)
+    assert evaluate(y, p, by_step=True, by_node=True)[0].shape == (2, 2)
+
+
+@needs_ref
+def test_metrics_match_reference():
+    ref = _ref("utils.math_utils")
+    from utils import math_utils as mine
+    rng = np.random.default_rng(0)
+    y = rng.normal(size=(17, 3, 5)); p = y + rng.normal(size=y.shape) * 0.3
+    y[0, 0, 0] = 0.0
+    for kw in ({}, {"by_step": True}, {"by_node": True}, {"by_step": True, "by_node": True}):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a, b = mine.evaluate(y, p, **kw), ref.evaluate(y, p, **kw)
+        for u, v in zip(a, b):
+            np.testing.assert_allclose(u, v, rtol=1e-12)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        np.testing.assert_allclose(mine.masked_MAPE(y, p), ref.masked_MAPE(y, p))
+
+
+# ---- dataloader --------------------------------------------------------------------------------------
+def test_dataset_windows_and_normalisation():
+    from data_loader.forecast_dataloader import ForecastDataset, de_normalized, normalized
+    data = np.arange(40, dtype=np.float64).reshape(20, 2)
+    ds = ForecastDataset(data, window_size=4, horizon=2)
+    assert len(ds) == 20 - 4 - 2 + 1
+    x, y = ds[3]
+    assert x.dtype == torch.float32 and x.shape == (4, 2) and y.shape == (2, 2)
+    np.testing.assert_array_equal(x.numpy(), data[3:7]); np.testing.assert_array_equal(y.numpy(), data[7:9])
+    assert len(ForecastDataset(data, 4, 2, interval=3)) == 15 // 3
+    st = {"mean": data.mean(0).tolist(), "std": [0.0, data[:, 1].std()]}
+    z, st2 = normalized(data, "z_score", st)
+    assert st2["std"][0] == 1                                           # zero std replaced by 1
+    np.testing.assert_allclose(de_normalized(z, "z_score", st2), data)
+    mm, s3 = normalized(data, "min_max")
+    assert mm.min() == 0.0 and mm.max() <= 1.0
+    np.testing.assert_allclose(de_normalized(mm, "min_max", s3), data, atol=1e-3)
+
+
+@needs_ref
+@pytest.mark.parametrize("method", [None, "z_score", "min_max"])
+def test_dataset_matches_reference(method):
+    ref = _ref("data_loader.forecast_dataloader")
+    from data_loader import forecast_dataloader as mine
+    rng = np.random.default_rng(1)
+    data = rng.normal(size=(60, 7))
+    data[0, 0] = np.nan; data[10:13, 2] = np.nan; data[-1, 6] = np.nan
+    stat = None
+    if method == "z_score":
+        stat = {"mean": np.nanmean(data, 0).tolist(), "std": np.nanstd(data, 0).tolist()}
+    if method == "min_max":
+        # (the reference cannot subtract the list statistics its own handler writes; use arrays)
+        stat = {"min": np.nanmin(data, 0), "max": np.nanmax(data, 0)}
+    a = mine.ForecastDataset(data.copy(), 12, 3, method, dict(stat) if stat else None, interval=2)
+    b = ref.ForecastDataset(data.copy(), 12, 3, method, dict(stat) if stat else None, interval=2)
+    assert len(a) == len(b) and a.x_end_idx == b.x_end_idx
+    for i in (0, 5, len(a) - 1):
+        for u, v in zip(a[i], b[i]):
+            assert torch.equal(u, v)
+    if method:
+        z = rng.normal(size=(4, 3, 7))
+        np.testing.assert_allclose(mine.de_normalized(z, method, dict(stat)), ref.de_normalized(z, method, dict(stat)))
+
+
+# ---- handler: rolling inference / validate with a stub model ---------------------------------------------
+class _StubModel(torch.nn.Module):
+    """Emits `emit` steps per call: the mean of the window plus the step index."""
+    def __init__(self, emit):
+        super().__init__()
+        self.emit = emit
+        self.calls = 0
+
+    def forward(self, x):
+        self.calls += 1
+        base = x.mean(dim=1, keepdim=True)
+        out = torch.cat([base + 0.1 * (i + 1) for i in range(self.emit)], dim=1)
+        return out, None
+
+
+def _loader(n=23, N=5, W=12, H=3, bs=8):
+    from data_loader.forecast_dataloader import ForecastDataset
+    data = np.random.default_rng(2).normal(size=(n + W + H, N))
+    return torch.utils.data.DataLoader(ForecastDataset(data, W, H), batch_size=bs, shuffle=False)
+
+
+@pytest.mark.parametrize("emit", [3, 1, 2])
+def test_inference_rolls_the_window(emit):
+    from models import handler
+    m = _StubModel(emit)
+    loader = _loader()
+    f, t = handler.inference(m, loader, "cpu", 5, 12, 3)
+    assert f.shape == t.shape == (len(loader.dataset), 3, 5)
+    assert m.calls == len(loader) * int(np.ceil(3 / emit))
+    if ref_shim.reference_available():
+        rh = _ref("models.handler")
+        f2, t2 = rh.inference(_StubModel(emit), _loader(), "cpu", 5, 12, 3)
+        np.testing.assert_allclose(f, f2); np.testing.assert_allclose(t, t2)
+
+
+def test_validate_writes_csvs_and_scores(tmp_path, capsys):
+    from models import handler
+    stat = {"mean": [0.5] * 5, "std": [2.0] * 5}
+    out = handler.validate(_StubModel(3), _loader(), "cpu", "z_score", stat, 5, 12, 3, result_file=str(tmp_path))
+    assert set(out) == {"mae", "mae_node", "mape", "mape_node", "rmse", "rmse_node"}
+    assert out["mae_node"].shape == (5,)
+    for name in ("target", "predict", "predict_abs_error", "predict_ape"):
+        assert (tmp_path / f"{name}.csv").exists()
+    assert "RAW : MAPE" in capsys.readouterr().out
+
+
+def test_save_load_roundtrip_and_epoch_naming(tmp_path):
+    from models import handler
+    m = torch.nn.Linear(3, 2)
+    handler.save_model(m, str(tmp_path), 0)          # epoch 0 -> the "best" file name (reference quirk)
+    handler.save_model(m, str(tmp_path), 4)
+    assert (tmp_path / "_stemgnn.pt").exists() and (tmp_path / "4_stemgnn.pt").exists()
+    m2 = handler.load_model(str(tmp_path))
+    assert torch.equal(m2.weight, m.weight)
+    assert handler.load_model(str(tmp_path / "nope")) is None
+
+
+def test_model_state_dict_matches_reference_layout():
+    """Drop-in Model: same keys/shapes as the reference state_dict and picklable."""
+    import pickle
+    from models.base_model import Model
+    from oracle import torch_port as tp
+    m = Model(23, 2, 12, 5, horizon=3)
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == tp.param_shapes(23, 12, 3)
+    assert sum(p.numel() for p in m.parameters()) == 3 * 23 * 23 + 3 * 23 * 12 + 8 * 23 + 2 * 528708 + 732 + 156 + 39
+    m2 = pickle.loads(pickle.dumps(m))
+    assert torch.equal(m2.weight_key, m.weight_key)
+    if ref_shim.reference_available():
+        ref = ref_shim.build_reference_model(23, 12, 5, 3)
+        assert list(ref.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(ref.state_dict())           # reference checkpoints load
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 12, 23))
+    with pytest.raises(ValueError):
+        Model(23, 3, 12, 5)
+
+
+# ---- C ABI surface -------------------------------------------------------------------------------------
+def test_c_abi_exports_every_declared_symbol():
+    from stemgnn_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "stemgnn_b200.h")).read()
+    declared = set(re.findall(r"\b(stemgnn_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.stemgnn_version() == 1
+    d = _lib.Dims(32, 358, 12, 3, 5)
+    import ctypes
+    ev, tr = lib.stemgnn_workspace_bytes(ctypes.byref(d), 0), lib.stemgnn_workspace_bytes(ctypes.byref(d), 1)
+    assert 0 < ev < tr
+    bad = _lib.Dims(0, 358, 12, 3, 5)
+    assert lib.stemgnn_workspace_bytes(ctypes.byref(bad), 0) == 0
+
+
+def test_c_abi_rejects_bad_arguments_without_gpu():
+    import ctypes
+    from stemgnn_b200 import _lib
+    lib = _lib.load()
+    d = _lib.Dims(4, 8, 12, 3, 5)
+    rc = lib.stemgnn_model_forward(ctypes.byref(d), None, None, None, None, None, None, None, 0, None)
+    assert rc != 0 and b"null" in lib.stemgnn_last_error()
+    with pytest.raises(RuntimeError, match="stemgnn_b200"):
+        _lib.check(rc, "forward")
