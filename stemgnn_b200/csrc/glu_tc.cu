@@ -1,9 +1,295 @@
-// tcgen05 TF32 GLU GEMM — placeholder until the tensor-core kernel lands (returns "unsupported").
+// GLU layer on the 5th-generation tensor cores (tcgen05, TF32 operands, fp32 accumulation in TMEM).
+//
+//   out[M,N] = (A[M,K] Wl[N,K]^T + bl) * sigmoid(A Wr^T + br)          (reference base_model.py:12-13)
+//
+// This is 61 % of the forward flops of the hot path (the 12 GLU Linear layers per block).
+// One CTA owns a 128-row tile of A and BOTH weight matrices, so the left and right pre-activations of a
+// row live side by side in tensor memory (columns [0,N) and [256,256+N)) and the gate is applied in
+// the TMEM->register epilogue without a round trip through HBM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled K-major tiles of
+// A / Wl / Wr, OOB rows & K-tail zero-filled by the TMA unit), warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer (kind::tf32, M=128, N<=256, K=8 per instruction), warps 2-5 = epilogue
+// (tcgen05.ld 32x32b -> bias + gate -> global).  Two-stage smem ring with full/empty mbarriers;
+// tcgen05.commit releases stages and publishes the finished accumulator.
+//
+// Operand precision: fp32 bit patterns are fed directly; kind::tf32 reads the top 19 bits
+// (truncation).  Error budget vs the fp32 reference: DESIGN.md "Precision".
+#include <cuda.h>
+
 #include "common.cuh"
 #include "internal.cuh"
+
 namespace sg {
-int glu_gemm_tc(int, int, int, const float*, int, const float*, const float*, const float*, const float*,
-                float*, int, float*, float*, int, cudaStream_t) {
-  return -1;
+
+namespace {
+
+constexpr int TC_BM = 128;            // rows per CTA (UMMA M)
+constexpr int TC_BK = 32;             // fp32 elements per stage along K = one 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_RIGHT_COL = 256;     // TMEM column of the right accumulator
+constexpr uint32_t TC_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();   // bring-up guard: a lost arrival must fail, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);        // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset = 1024 bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M=128
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct GluTcArgs {
+  const float* bl; const float* br;
+  float* out; int ldo;
+  float* save_l; float* save_s; int lds;
+  int M, N, K;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wl,
+              const __grid_constant__ CUtensorMap map_wr, GluTcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle pattern
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int N = g.N;
+  const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)N * 128;
+  const uint32_t stage_bytes = a_bytes + 2 * w_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wr)) : "memory");
+  }
+  if (warp == 1) {   // the allocating warp also owns the dealloc
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_2d(st, &map_a, &full_bar[s], kb * TC_BK, m0);
+        tma_load_2d(st + a_bytes, &map_wl, &full_bar[s], kb * TC_BK, 0);
+        tma_load_2d(st + a_bytes + w_bytes, &map_wr, &full_bar[s], kb * TC_BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_tf32(N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t wl_addr = a_addr + a_bytes, wr_addr = wl_addr + w_bytes;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {   // 8 tf32 = 32 bytes along K per instruction
+          const uint64_t ad = umma_desc_sw128(a_addr + kk * 32);
+          const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, ad, umma_desc_sw128(wl_addr + kk * 32), idesc, acc);
+          umma_tf32(tmem_base + TC_RIGHT_COL, ad, umma_desc_sw128(wr_addr + kk * 32), idesc, acc);
+        }
+        umma_commit(&empty_bar[s]);                 // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);                   // accumulators complete
+    }
+  } else {             // ===== epilogue: warps 2..5 =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
+    const int row = m0 + quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+      float l[16], r[16];
+      tmem_ld16(taddr + c, l);
+      tmem_ld16(taddr + TC_RIGHT_COL + c, r);
+      tmem_ld_wait();
+      if (row < g.M) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          l[j] += __ldg(g.bl + c + j);
+          r[j] = __fdividef(1.0f, 1.0f + __expf(-(r[j] + __ldg(g.br + c + j))));
+          o[j] = l[j] * r[j];
+        }
+        float4* po = reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) po[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        if (g.save_l != nullptr) {
+          float4* pl = reinterpret_cast<float4*>(g.save_l + (size_t)row * g.lds + c);
+          float4* ps = reinterpret_cast<float4*>(g.save_s + (size_t)row * g.lds + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pl[j] = make_float4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+            ps[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor (rows x cols, row stride ld elements), box = box_rows x 32 cols, 128B swizzle
+bool make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, const float* bl,
+                const float* Wr, const float* br, float* out, int ldo, float* save_l, float* save_s,
+                int lds, cudaStream_t st) {
+  // shape / alignment envelope of this kernel; anything else takes the fp32 FFMA2 path
+  if (N % 16 != 0 || N < 16 || N > 256 || K < 1 || (K & 3) != 0 || (lda & 3) != 0 || (ldo & 3) != 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wl) & 15) ||
+      (reinterpret_cast<uintptr_t>(Wr) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(bl) & 3))
+    return -1;
+  if (save_l != nullptr && ((lds & 3) || (reinterpret_cast<uintptr_t>(save_l) & 15) ||
+                            (reinterpret_cast<uintptr_t>(save_s) & 15)))
+    return -1;
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -1;
+  CUtensorMap ma, ml, mr;
+  if (!make_map(enc, &ma, A, M, K, lda, TC_BM) || !make_map(enc, &ml, Wl, N, K, K, N) ||
+      !make_map(enc, &mr, Wr, N, K, K, N))
+    return -1;
+  const size_t smem = (size_t)TC_STAGES * (TC_BM * 128 + 2 * (size_t)N * 128) + 64 + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  GluTcArgs g = {bl, br, out, ldo, save_l, save_s, lds, M, N, K};
+  glu_tc_kernel<<<ceil_div(M, TC_BM), TC_THREADS, smem, st>>>(ma, ml, mr, g);
+  SG_LAUNCH_CHECK("glu_tc_kernel");
+  return 0;
+}
+
 }  // namespace sg

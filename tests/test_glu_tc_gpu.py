@@ -1,0 +1,65 @@
+"""tcgen05 TF32 GLU GEMM: unit parity against an fp64 reference and end-to-end parity of the whole
+forward with the tensor-core path forced on (north_star tolerance rtol 1e-3 / atol 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_port as tp
+from tests.helpers import assert_close, build_model, cases, golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _glu(M, N, K, use_tc, seed=0, lda=None):
+    from stemgnn_b200 import _lib, runtime
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(seed)
+    lda = lda or K
+    A = torch.randn(M, lda, generator=g)
+    Wl = torch.randn(N, K, generator=g) / K ** 0.5
+    Wr = torch.randn(N, K, generator=g) / K ** 0.5
+    bl, br = torch.randn(N, generator=g) * 0.1, torch.randn(N, generator=g) * 0.1
+    Ad, Wld, Wrd, bld, brd = (t.to(DEV) for t in (A, Wl, Wr, bl, br))
+    out = torch.full((M, N), float("nan"), device=DEV)
+    rc = lib.stemgnn_glu_gemm(M, N, K, Ad.data_ptr(), lda, Wld.data_ptr(), bld.data_ptr(), Wrd.data_ptr(),
+                              brd.data_ptr(), out.data_ptr(), N, use_tc, runtime._stream_ptr(torch.device(DEV)))
+    _lib.check(rc, "glu_gemm")
+    torch.cuda.synchronize()
+    a = A[:, :K].double()
+    ref = (a @ Wl.double().t() + bl.double()) * torch.sigmoid(a @ Wr.double().t() + br.double())
+    return out.cpu(), ref.float()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 240, 32), (128, 240, 64), (100, 64, 32), (300, 64, 64), (4097, 240, 36),
+                                   (11456, 240, 240), (11456, 240, 36), (77, 16, 8), (513, 256, 100)])
+def test_glu_tc_matches_fp64_reference(M, N, K):
+    out, ref = _glu(M, N, K, 1, seed=M + N + K)
+    assert torch.isfinite(out).all()
+    # TF32 operands (10-bit mantissa, truncated): relative error ~ 2^-10 per product, averaged over K
+    assert_close(out, ref, rtol=5e-3, atol=8e-3, msg=f"tc glu {M}x{N}x{K}")
+    err = (out - ref).abs().max().item()
+    out32, _ = _glu(M, N, K, 0, seed=M + N + K)
+    err32 = (out32 - ref).abs().max().item()
+    print(f"M={M} N={N} K={K}: max|err| tf32={err:.2e} fp32={err32:.2e}")
+    assert err < 1e-2
+
+
+def test_glu_tc_strided_A():
+    out, ref = _glu(260, 240, 240, 1, seed=9, lda=480)
+    assert_close(out, ref, rtol=4e-3, atol=4e-3, msg="tc glu strided")
+
+
+@pytest.mark.parametrize("name", ["tiny_taps", "odd_h1_taps", "multi2_w8", "cfg1_shape", "cfg1_trained", "cfg2_shape"])
+def test_model_forward_tensor_core_path_vs_reference_golden(name):
+    from stemgnn_b200 import runtime
+    c = cases("forward")[name]
+    g = golden(name)
+    m = build_model(c, DEV).eval()
+    m.gemm_mode = runtime.GEMM_TC
+    x, _ = tp.synthetic_batch(c["B"], c["N"], c["W"], c["H"], seed=1234)
+    with torch.no_grad():
+        forecast, attention = m(x.to(DEV))
+    assert_close(forecast, g["forecast"], msg=name + " forecast (tcgen05 TF32 GLU chain)")
+    err = np.abs(forecast.cpu().numpy() - g["forecast"])
+    print(f"{name}: forecast max|err| = {err.max():.2e}, MAE vs reference = {err.mean():.2e}")
