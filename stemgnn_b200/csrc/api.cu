@@ -46,6 +46,10 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
   ws.row_m = training ? take(R) : nullptr;
   ws.row_zinv = training ? take(R) : nullptr;
   ws.h_all = training ? take(N * R) : nullptr;
+  ws.g_r = training ? take(N * R) : nullptr;
+  ws.g_z = training ? take(N * R) : nullptr;
+  ws.g_n = training ? take(N * R) : nullptr;
+  ws.g_hn = training ? take(N * R) : nullptr;
   for (int i = 0; i < STEMGNN_MAX_STACK; ++i) {
     BlockWs& b = ws.blk[i];
     b.G = take(R * 4 * W);              // 3W columns on the model path, 4W for the stage API
@@ -65,6 +69,20 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
       b.save_s[g] = training ? take(R * d) : nullptr;
     }
     b.fs = training ? take(R * T) : nullptr;
+  }
+  if (training) {
+    BwdWs& w = ws.bwd;
+    const size_t H = dm.H;
+    w.h_fsum = take(R * W); w.h_act = take(R * W); w.h_dhj = take(R * W); w.h_dout = take(R * H);
+    w.d_fsum = take(R * W);
+    w.d_pre = take(R * (T + W)); w.negdz = take(R * W); w.d_act3 = take(R * 2 * d);
+    w.d_wout = take(8 * T * (T + W)); w.d_ri = take(8 * T * T); w.d_w1f = take(4 * d * 3 * W);
+    w.dlr = take(R * 2 * d); w.d_act[0] = take(R * d); w.d_act[1] = take(R * d);
+    w.d_G = take(R * 3 * W); w.d_Gp = take(R * 3 * W);
+    w.d_bc = take(R * W); w.d_x0 = take(R * W); w.d_mul_L = take(4 * N * N);
+    w.dAsym = take(N * N); w.ddeg = take(N); w.dA = take(N * N);
+    w.dots = take(R); w.d_key = take(R); w.d_query = take(R);
+    w.dgh = take(N * R * 3); w.dh[0] = take(R); w.dh[1] = take(R); w.d_xs = take(N * B * W);
   }
   ws.floats = off;
   return ws;
@@ -263,7 +281,7 @@ int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
 
   SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dm.B, dm.W, dm.N, st));
   GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
-                p->weight_query, ws.key, ws.query, ws.h_all, ws.gi, dm.B, dm.N, dm.W};
+                p->weight_query, ws.key, ws.query, ws.h_all, ws.gi, ws.g_r, ws.g_z, ws.g_n, ws.g_hn, dm.B, dm.N, dm.W};
   SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
   SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
   SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, ws.x_bnw, x, ws.mul_L, ws.blk[0], st));
@@ -290,7 +308,7 @@ int stemgnn_gru_keyquery_forward(const stemgnn_dims_t* dims, const stemgnn_param
   Workspace ws = carve_workspace(*dims, 0, static_cast<float*>(workspace));
   SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dims->B, dims->W, dims->N, st));
   GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
-                p->weight_query, key, query, gru_out, ws.gi, dims->B, dims->N, dims->W};
+                p->weight_query, key, query, gru_out, ws.gi, nullptr, nullptr, nullptr, nullptr, dims->B, dims->N, dims->W};
   return gru_keyquery_forward(ga, path, ws.gru_scratch, st);
 }
 

@@ -21,6 +21,7 @@ struct GemmOperands {
   const float* B; int ldb; long long sB;
   const float* B2;                          // second B operand (DUAL), same ldb / sB
   int M, N, K;
+  int ksplit;                               // > 1: blockIdx.z splits K (no batching); epilogue must be atomic
 };
 
 __device__ __forceinline__ float4 ld4_guard(const float* base, long long off, int valid, bool vec) {
@@ -45,7 +46,15 @@ __global__ void __launch_bounds__(GM_THREADS) sgemm_kernel(GemmOperands g, Epi e
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int z = blockIdx.z;
+  const bool split = g.ksplit > 1;
+  const int z = split ? 0 : blockIdx.z;
+  int k_lo = 0, k_hi = g.K;
+  if (split) {
+    const int chunk = ((g.K + g.ksplit - 1) / g.ksplit + GM_BK - 1) / GM_BK * GM_BK;
+    k_lo = blockIdx.z * chunk;
+    k_hi = min(g.K, k_lo + chunk);
+    if (k_lo >= k_hi) return;
+  }
   const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
   const float* __restrict__ A = g.A + (long long)z * g.sA;
   const float* __restrict__ B = g.B + (long long)z * g.sB;
@@ -62,25 +71,25 @@ __global__ void __launch_bounds__(GM_THREADS) sgemm_kernel(GemmOperands g, Epi e
       if (!A_KM) {
         const int row = gid >> 2, kq = gid & 3;
         const int m = m0 + row, k = k0 + kq * 4;
-        const int valid = (m < g.M) ? max(0, min(4, g.K - k)) : 0;
+        const int valid = (m < g.M) ? max(0, min(4, k_hi - k)) : 0;
         ra[i] = ld4_guard(A, (long long)m * g.lda + k, valid, vecA);
       } else {
         const int kk = gid >> 5, mq = gid & 31;
         const int k = k0 + kk, m = m0 + mq * 4;
-        const int valid = (k < g.K) ? max(0, min(4, g.M - m)) : 0;
+        const int valid = (k < k_hi) ? max(0, min(4, g.M - m)) : 0;
         ra[i] = ld4_guard(A, (long long)k * g.lda + m, valid, vecA);
       }
     }
     if (B_NK) {
       const int col = tid >> 2, kq = tid & 3;
       const int n = n0 + col, k = k0 + kq * 4;
-      const int valid = (n < g.N) ? max(0, min(4, g.K - k)) : 0;
+      const int valid = (n < g.N) ? max(0, min(4, k_hi - k)) : 0;
       rb = ld4_guard(B, (long long)n * g.ldb + k, valid, vecB);
       if (DUAL) rb2 = ld4_guard(B2, (long long)n * g.ldb + k, valid, vecB);
     } else {
       const int kk = tid >> 4, nq = tid & 15;
       const int k = k0 + kk, n = n0 + nq * 4;
-      const int valid = (k < g.K) ? max(0, min(4, g.N - n)) : 0;
+      const int valid = (k < k_hi) ? max(0, min(4, g.N - n)) : 0;
       rb = ld4_guard(B, (long long)k * g.ldb + n, valid, vecB);
       if (DUAL) rb2 = ld4_guard(B2, (long long)k * g.ldb + n, valid, vecB);
     }
@@ -126,13 +135,13 @@ __global__ void __launch_bounds__(GM_THREADS) sgemm_kernel(GemmOperands g, Epi e
     if (DUAL) acc2[i][0] = acc2[i][1] = make_float2(0.f, 0.f);
   }
 
-  const int nk = (g.K + GM_BK - 1) / GM_BK;
-  load_tiles(0);
+  const int nk = (k_hi - k_lo + GM_BK - 1) / GM_BK;
+  load_tiles(k_lo);
   store_tiles(0);
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * GM_BK);
+    if (kt + 1 < nk) load_tiles(k_lo + (kt + 1) * GM_BK);
 #pragma unroll
     for (int kk = 0; kk < GM_BK; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
@@ -252,10 +261,33 @@ struct EpiGlu {
   }
 };
 
+// C += alpha * AB with atomics (split-K partial sums; gradients accumulate by contract)
+struct EpiAtomicAdd {
+  float* C; int ldc;
+  float alpha;
+  __device__ __forceinline__ void store4(int, int m, int n, int valid, float4 v, float4) const {
+    float* c = C + (long long)m * ldc + n;
+    if (valid > 0) atomicAdd(c, alpha * v.x);
+    if (valid > 1) atomicAdd(c + 1, alpha * v.y);
+    if (valid > 2) atomicAdd(c + 2, alpha * v.z);
+    if (valid > 3) atomicAdd(c + 3, alpha * v.w);
+  }
+};
+
+// number of K-splits that brings a (M x N x K) product to about two waves of CTAs
+inline int pick_ksplit(int M, int N, int K) {
+  const int tiles = ceil_div(M, GM_BM) * ceil_div(N, GM_BN);
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int maxs = K / (4 * GM_BK) > 0 ? K / (4 * GM_BK) : 1;
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
 template <bool A_KM, bool B_NK, bool DUAL, class Epi>
 inline int launch_sgemm(const GemmOperands& g, const Epi& epi, int batch, cudaStream_t st,
                         const char* name) {
   if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
+  if (g.ksplit > 1) batch = g.ksplit;
   dim3 grid(ceil_div(g.N, GM_BN), ceil_div(g.M, GM_BM), batch);
   sgemm_kernel<A_KM, B_NK, DUAL, Epi><<<grid, GM_THREADS, 0, st>>>(g, epi);
   SG_LAUNCH_CHECK(name);

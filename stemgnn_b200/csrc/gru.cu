@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
   extern __shared__ __align__(16) float smem[];
   float* Wsm = smem;                              // [3*ULOC][KP]
   float* hbuf = Wsm + 3 * ULOC * KP;              // [2][BC][KP]
-  float* stage = hbuf + 2 * BC * KP;              // [BC][32]
-  float* sums = stage + BC * 32;                  // [WARPS][V]
+  float* stage = hbuf + 2 * BC * KP;              // [5][BC][32]: new h, and (training) r, z, n, hn
+  float* sums = stage + 5 * BC * 32;              // [WARPS][V]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
@@ -213,6 +213,12 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
         hn = (1.f - zt) * nt + zt * hprev;
         key_acc = fmaf(hn, wk_s, key_acc);
         query_acc = fmaf(hn, wq_s, query_acc);
+        if (a.g_r != nullptr) {   // gate values for BPTT
+          stage[(1 * BC + fb) * 32 + lu] = r;
+          stage[(2 * BC + fb) * 32 + lu] = zt;
+          stage[(3 * BC + fb) * 32 + lu] = nt;
+          stage[(4 * BC + fb) * 32 + lu] = gh_n + bhn;
+        }
       }
       stage[fb * 32 + lu] = hn;
     }
@@ -227,8 +233,16 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
           remote[(nxt * BC + bb) * KP + u0 + lane] = stage[bb * 32 + lane];
       }
     }
-    if (a.h_all != nullptr && w < BC && (b0 + w) < B && lane < U && (u0 + lane) < N)
-      a.h_all[((long long)s * B + (b0 + w)) * N + u0 + lane] = stage[w * 32 + lane];
+    if (a.h_all != nullptr && w < BC && (b0 + w) < B && lane < U && (u0 + lane) < N) {
+      const long long o = ((long long)s * B + (b0 + w)) * N + u0 + lane;
+      a.h_all[o] = stage[w * 32 + lane];
+      if (a.g_r != nullptr) {
+        a.g_r[o] = stage[(1 * BC + w) * 32 + lane];
+        a.g_z[o] = stage[(2 * BC + w) * 32 + lane];
+        a.g_n[o] = stage[(3 * BC + w) * 32 + lane];
+        a.g_hn[o] = stage[(4 * BC + w) * 32 + lane];
+      }
+    }
     // (f) one cluster barrier per step: all slices of h_s are visible before step s+1 reads them
     __syncwarp();
     cluster_arrive_release();
@@ -248,7 +262,7 @@ static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, int* max_active
   constexpr int KP = 128 * JC;
   constexpr int ULOC = GRU_WARPS * UPW;
   const size_t smem =
-      (size_t)(3 * ULOC * KP + 2 * BC * KP + BC * 32 + GRU_WARPS * 3 * UPW * BC) * sizeof(float);
+      (size_t)(3 * ULOC * KP + 2 * BC * KP + 5 * BC * 32 + GRU_WARPS * 3 * UPW * BC) * sizeof(float);
   auto kern = gru_cluster_kernel<JC, UPW, CS, BC>;
   static bool attr_set = false;   // one process drives one device (DDP = process per GPU)
   static int max_clusters = 0;
@@ -350,6 +364,10 @@ __global__ void __launch_bounds__(128) gru_step_kernel(GruArgs a, int s, const f
       const float hn = (1.f - zt) * nt + zt * h_prev[(long long)bi * N + u];
       h_next[(long long)bi * N + u] = hn;
       if (a.h_all != nullptr) a.h_all[((long long)s * B + bi) * N + u] = hn;
+      if (a.g_r != nullptr) {
+        const long long o = ((long long)s * B + bi) * N + u;
+        a.g_r[o] = r; a.g_z[o] = zt; a.g_n[o] = nt; a.g_hn[o] = gh_n + __ldg(a.b_hh + 2 * N + u);
+      }
       // key/query accumulate in place (this thread is the only writer of (bi,u))
       a.key[(long long)bi * N + u] = fmaf(hn, wk_s, a.key[(long long)bi * N + u]);
       a.query[(long long)bi * N + u] = fmaf(hn, wq_s, a.query[(long long)bi * N + u]);

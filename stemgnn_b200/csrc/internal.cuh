@@ -17,6 +17,7 @@ struct GruArgs {
   float* query;        // (B, N)
   float* h_all;        // (N, B, N) or null
   float* gi;           // (N, B, 3N) scratch: input projection of every step
+  float* g_r; float* g_z; float* g_n; float* g_hn;   // (N, B, N) gate values saved for BPTT (or null)
   int B, N, W;
 };
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
@@ -87,9 +88,17 @@ struct BlockWs {
   float* save_l[6]; float* save_s[6];   // training: GLU left pre-activation / gate per GLU index
   float* fs;       // training: forecast_source (R, T)
 };
+// scratch of the backward pass (training workspaces only)
+struct BwdWs {
+  float *h_fsum, *h_act, *h_dhj, *h_dout, *d_fsum;      // model head
+  float *d_pre, *negdz, *d_act3, *d_wout, *d_ri, *d_w1f, *dlr, *d_act[2], *d_G, *d_Gp;   // block (reused)
+  float *d_bc, *d_x0, *d_mul_L, *dAsym, *ddeg, *dA, *dots, *d_key, *d_query;
+  float *dgh, *dh[2], *d_xs;
+};
 struct Workspace {
   float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
-  float *row_m, *row_zinv, *h_all;
+  float *row_m, *row_zinv, *h_all, *g_r, *g_z, *g_n, *g_hn;
+  BwdWs bwd;
   BlockWs blk[STEMGNN_MAX_STACK];
   size_t floats;
 };

@@ -1,0 +1,166 @@
+"""GPU parity of the CUDA backward (one C-ABI call) against (a) gradient goldens minted from the
+unmodified reference with autograd and (b) autograd through the torch port of the reference on the host."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_port as tp
+from tests.helpers import assert_close, build_model, case_params, cases, golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel_check(name, got, want, rtol=2e-3):
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else got
+    want = want.detach().cpu().numpy() if torch.is_tensor(want) else want
+    scale = max(float(np.abs(want).max()), 1e-12)
+    err = float(np.abs(got - want).max())
+    assert err <= rtol * scale + 1e-9, f"{name}: max|err| {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e})"
+    return err / scale
+
+
+def _run(c, mask, gemm_mode, seed_xy=4321):
+    from stemgnn_b200 import runtime
+    m = build_model(c, DEV)
+    m.gemm_mode = gemm_mode
+    x, y = tp.synthetic_batch(c["B"], c["N"], c["W"], c["H"], seed=seed_xy)
+    xd = x.to(DEV).requires_grad_(True)
+    if mask is None:
+        m.eval()
+        forecast, attention = m(xd)
+    else:
+        m.train()
+        forecast, attention = m(xd, dropout_mask=mask)
+    loss = torch.nn.functional.mse_loss(forecast, y.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    return m, xd, forecast, float(loss)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("name", ["grad_multi2", "grad_tiny", "grad_dropmask"])
+def test_backward_vs_reference_gradient_golden(name, mode):
+    from stemgnn_b200 import runtime
+    c = cases("grad")[name]
+    g = golden(name)
+    mask = None
+    if c["p_drop"] is not None:
+        gen = torch.Generator().manual_seed(99)
+        mask = (torch.rand(c["B"], c["N"], c["N"], generator=gen) >= c["p_drop"])
+    m, xd, forecast, loss = _run(c, mask, runtime.GEMM_FP32 if mode == "fp32" else runtime.GEMM_TC)
+    rtol = 2e-3 if mode == "fp32" else 1e-2
+    assert abs(loss - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    assert_close(forecast, g["forecast"], msg="forecast")
+    _rel_check("grad.x", xd.grad, g["grad.x"], rtol)
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k in g.files:
+        if k.startswith("grad.") and k != "grad.x":
+            worst = max(worst, _rel_check(k, named[k[5:]].grad, g[k], rtol))
+        elif k.startswith("gradsample."):
+            worst = max(worst, _rel_check(k, named[k[11:]].grad.reshape(-1)[::53], g[k], rtol))
+        elif k.startswith("gradsum."):
+            flat = named[k[8:]].grad.double().reshape(-1)
+            assert abs(float(flat.sum()) - g[k][0]) <= 5e-3 * g[k][1] + 1e-9, k
+        elif k.startswith("nograd."):
+            gr = named[k[7:]].grad
+            assert gr is None or float(gr.abs().max()) == 0.0, k
+    print(f"{name}[{mode}]: worst relative gradient error {worst:.2e}")
+
+
+@pytest.mark.parametrize("B,N,H,drop", [(32, 140, 3, False), (29, 140, 3, True), (32, 358, 3, True), (8, 53, 12, True)])
+def test_backward_vs_port_autograd(B, N, H, drop):
+    """cfg1 / cfg2 shapes (incl. the ragged last batch 29 of ECG): every parameter gradient against
+    autograd through the reference-ordered torch port on the host CPU."""
+    from stemgnn_b200 import runtime
+    c = dict(B=B, N=N, W=12, H=H, multi=5, pseed=300 + N + B, mode="trained")
+    mask = None
+    if drop:
+        mask = (torch.rand(B, N, N, generator=torch.Generator().manual_seed(7)) >= 0.5)
+    m, xd, forecast, loss = _run(c, mask, runtime.GEMM_FP32, seed_xy=11)
+    p = {k: v.clone().requires_grad_(True) for k, v in case_params(c).items()}
+    x, y = tp.synthetic_batch(B, N, 12, H, seed=11)
+    x.requires_grad_(True)
+    f_ref, _ = tp.model_forward(x, p, dropout_mask=mask.float() if drop else None, dropout_p=0.5)
+    l_ref = torch.nn.functional.mse_loss(f_ref, y)
+    l_ref.backward()
+    assert abs(loss - float(l_ref)) < 1e-5 * max(1.0, float(l_ref))
+    _rel_check("grad.x", xd.grad, x.grad)
+    named = dict(m.named_parameters())
+    worst = ("", 0.0)
+    for k, v in p.items():
+        if v.grad is None:
+            assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
+            continue
+        r = _rel_check(k, named[k].grad, v.grad)
+        if r > worst[1]:
+            worst = (k, r)
+    print(f"B={B} N={N}: worst relative gradient error {worst[1]:.2e} at {worst[0]}")
+
+
+def test_attention_output_gradient_flows():
+    """A loss on the returned attention matrix (handler.py ignores it, autograd must not)."""
+    from stemgnn_b200 import runtime
+    c = dict(B=4, N=24, W=12, H=3, multi=2, pseed=5, mode="trained")
+    m = build_model(c, DEV).eval()
+    m.gemm_mode = runtime.GEMM_FP32
+    x, y = tp.synthetic_batch(4, 24, 12, 3, seed=3)
+    wgt = torch.randn(24, 24, generator=torch.Generator().manual_seed(2))
+    f, a = m(x.to(DEV))
+    ((a * wgt.to(DEV)).sum() + f.square().mean()).backward()
+    p = {k: v.clone().requires_grad_(True) for k, v in case_params(c).items()}
+    f2, a2 = tp.model_forward(x, p)
+    ((a2 * wgt).sum() + f2.square().mean()).backward()
+    named = dict(m.named_parameters())
+    for k in ("weight_key", "weight_query", "GRU.weight_hh_l0", "GRU.weight_ih_l0", "GRU.bias_hh_l0"):
+        _rel_check(k, named[k].grad, p[k].grad)
+
+
+def test_training_steps_match_port():
+    """Five RMSprop steps (handler.py:126,160-165) with explicit dropout masks: the loss trajectory of
+    the CUDA path tracks the reference-ordered port."""
+    from stemgnn_b200 import runtime
+    c = dict(B=16, N=40, W=12, H=3, multi=5, pseed=77, mode="init")
+    m = build_model(c, DEV).train()
+    p = {k: v.clone().requires_grad_(True) for k, v in case_params(c).items()}
+    opt_d = torch.optim.RMSprop(m.parameters(), lr=1e-3, eps=1e-8)
+    opt_c = torch.optim.RMSprop(list(p.values()), lr=1e-3, eps=1e-8)
+    gen = torch.Generator().manual_seed(0)
+    losses_d, losses_c = [], []
+    for step in range(5):
+        x, y = tp.synthetic_batch(16, 40, 12, 3, seed=100 + step)
+        mask = (torch.rand(16, 40, 40, generator=gen) >= 0.5)
+        m.zero_grad()
+        f, _ = m(x.to(DEV), dropout_mask=mask)
+        ld = torch.nn.functional.mse_loss(f, y.to(DEV))
+        ld.backward()
+        opt_d.step()
+        opt_c.zero_grad()
+        f2, _ = tp.model_forward(x, p, dropout_mask=mask.float(), dropout_p=0.5)
+        lc = torch.nn.functional.mse_loss(f2, y)
+        lc.backward()
+        opt_c.step()
+        losses_d.append(float(ld)); losses_c.append(float(lc))
+    np.testing.assert_allclose(losses_d, losses_c, rtol=2e-3)
+    assert losses_d[-1] < losses_d[0] * 1.2
+
+
+def test_philox_training_is_reproducible_and_consistent():
+    """Philox dropout: same torch seed -> identical forward and gradients; the mask used by backward
+    is the one used by forward (gradient of a frozen-mask replay equals the recorded one)."""
+    c = dict(B=6, N=32, W=12, H=3, multi=2, pseed=9, mode="trained")
+    x, y = tp.synthetic_batch(6, 32, 12, 3, seed=1)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(123)
+        m = build_model(c, DEV).train()
+        f, a = m(x.to(DEV))
+        torch.nn.functional.mse_loss(f, y.to(DEV)).backward()
+        outs.append((f.detach().clone(), a.detach().clone(), m.GRU.weight_hh_l0.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert_close(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-9, msg="grad reproducibility")
+    m.eval()
+    with torch.no_grad():
+        f_eval, a_eval = m(x.to(DEV))
+    assert not torch.equal(a_eval, outs[0][1])          # dropout really was active in train mode
