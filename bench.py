@@ -200,10 +200,41 @@ def run_ours(args, rank, world, local_rank):
         e2e_s = time.perf_counter() - t0
         barrier()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- second column: training step (handler.py:160-165) = zero_grad + forward (train mode, Philox
+    #      dropout) + MSE + backward (+ the single flat-gradient all-reduce at N>1) + RMSprop ----------
+    from stemgnn_b200 import ddp
+    ddp.attach(model)
+    model.train()
+    y_dev = tp.synthetic_batch(B, N, W, H, seed=1234 + rank)[1].to(dev)
+    optim = torch.optim.RMSprop(model.parameters(), lr=1e-4, eps=1e-8)
+    crit = torch.nn.MSELoss()
+
+    def train_step():
+        model.zero_grad()
+        f, _a = model(x_dev)
+        loss = crit(f, y_dev)
+        loss.backward()
+        optim.step()
+        return loss
+
+    t_steps = max(5, min(args.steps, 20))
+    for _ in range(3):
+        train_step()
+    tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(t_steps)]
+    barrier()
+    for i in range(t_steps):
+        flush.zero_()
+        tev[i][0].record()
+        train_step()
+        tev[i][1].record()
+    barrier()
+    train_ms = sum(a.elapsed_time(b) for a, b in tev)
+    model.eval()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return
 
@@ -231,6 +262,10 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": B * W * N * 4, "d2h_bytes_per_step": B * H * N * 4,
                     "ms_per_step": e2e_ms / args.steps},
+            "train": {"value": world * B * t_steps / (train_ms * 1e-3), "unit": "windows/s",
+                      "ms_per_step": train_ms / t_steps, "steps": t_steps,
+                      "what": "zero_grad + forward(train, Philox dropout) + MSE + backward"
+                              + (" + flat-gradient NCCL all-reduce" if world > 1 else "") + " + RMSprop step"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": "windows/s", "cores": threads, "kind": "port",

@@ -144,6 +144,7 @@ class Model(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_rt"] = None
+        state.pop("_ddp", None)          # process groups are not picklable (whole-module checkpoints)
         return state
 
     def _apply(self, fn, *a, **kw):
@@ -222,8 +223,9 @@ class Model(nn.Module):
             mask = None
             if dropout_mask is not None:
                 mask = dropout_mask.to(device=x.device, dtype=torch.uint8).contiguous()
+            ddp_state = getattr(self, "_ddp", None)
             cfg = (self._dims(x.shape[0]), self.alpha, self.dropout_rate, use_dropout, seed, offset, mask,
-                   self.gemm_mode)
+                   self.gemm_mode, ddp_state if ddp_state and ddp_state.get("enabled") else None)
             forecast, attention = runtime.StemGNNFunction.apply(x, cfg, *rt["params"])
         if self.horizon == 1:
             return forecast.reshape(x.shape[0], 1, self.unit), attention

@@ -132,7 +132,7 @@ class StemGNNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg, *params):
-        dims, alpha, p_drop, use_dropout, seed, offset, mask, gemm_mode = cfg
+        dims, alpha, p_drop, use_dropout, seed, offset, mask, gemm_mode = cfg[:8]
         tensors = dict(zip(PARAM_KEYS, params))
         ptrs = build_ptrs(tensors)
         opts = make_opts(alpha, p_drop if use_dropout else 0.0, True, seed, offset,
@@ -175,6 +175,10 @@ class StemGNNFunction(torch.autograd.Function):
                                         ctx.ws.data_ptr(), ctx.ws.numel(), _stream_ptr(dev))
         _lib.check(rc, "stemgnn_model_backward")
         ctx.ws = None
+        ddp_group = ctx.cfg[8] if len(ctx.cfg) > 8 else None
+        if ddp_group is not None:                 # the ONE collective of a training step
+            from . import ddp
+            ddp.allreduce_mean_(flat, ddp_group.get("group"))
         # stock_block.1.backcast_short_cut.* never reaches the output (base_model.py:70-74): the
         # reference leaves its .grad as None
         out = [None if k.startswith("stock_block.1.backcast_short_cut") else g
