@@ -376,10 +376,20 @@ __global__ void __launch_bounds__(256) gru_bwd_step_kernel(GruBwdArgs a, int s, 
   const int k = k0 + kk;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (k < N) {
-    for (int row = sl; row < 3 * N; row += 8) {
-      const float w = __ldg(a.w_hh + (long long)row * N + k);
+    // 8 independent W_hh loads in flight per thread (the loop is L2-latency bound otherwise)
+    for (int row0 = sl; row0 < 3 * N; row0 += 64) {
+      float wv[8];
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) acc[bb] = fmaf(sgh[bb * 3 * N + row], w, acc[bb]);
+      for (int j = 0; j < 8; ++j) {
+        const int row = row0 + 8 * j;
+        wv[j] = row < 3 * N ? __ldg(a.w_hh + (long long)row * N + k) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = min(row0 + 8 * j, 3 * N - 1);
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) acc[bb] = fmaf(sgh[bb * 3 * N + row], wv[j], acc[bb]);
+      }
     }
   }
 #pragma unroll
