@@ -8,8 +8,10 @@
 //   * each CTA of a cluster owns ceil(N/16) hidden units: its 3*U rows of W_hh stay resident in
 //     shared memory for all N steps (persistent-RNN), so W_hh is read from HBM exactly once;
 //   * per step: packed-fp32 (FFMA2) mat-vec against the 4 hidden vectors, gate math, then the new
-//     hidden slice is scattered into every CTA's next-step buffer through DISTRIBUTED SHARED
-//     MEMORY and one cluster barrier; the input projection W_ih x_s + b_ih of all steps is one
+//     hidden slice is sent to every CTA's next-step buffer through DISTRIBUTED SHARED MEMORY with
+//     st.async stores that signal a per-buffer mbarrier in the destination CTA (no cluster-wide
+//     barrier on the critical path: a CTA starts step s+1 as soon as its 16 slices have landed);
+//     the input projection W_ih x_s + b_ih of all steps is one
 //     parallel GEMM beforehand (gru_input_proj) whose rows are prefetched a step ahead;
 //   * key/query (sum over steps of h_s * w[s]) are accumulated in registers, so the (N,B,N) GRU
 //     output is never materialised in eval mode (it is written only when the backward needs it).
@@ -33,6 +35,44 @@ __device__ __forceinline__ void cluster_arrive_release() {
 }
 __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 16-byte remote store that signals `bytes` on the destination CTA's mbarrier when it lands
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)),
+               "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();   // a lost signal must fail loudly, never hang the GPU
+  }
 }
 
 // Warp-wide sum of C values per lane (C a power of two <= 32) by recursive halving: after log2(C)
@@ -102,6 +142,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
   float* hbuf = Wsm + 3 * ULOC * KP;              // [2][BC][KP]
   float* stage = hbuf + 2 * BC * KP;              // [5][BC][32]: new h, and (training) r, z, n, hn
   float* sums = stage + 5 * BC * 32;              // [WARPS][V]
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(sums + GRU_WARPS * V);   // [2] one mbarrier per h buffer
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
@@ -109,19 +150,33 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int N = a.N, B = a.B;
   const int U = (N + CS - 1) / CS;
+  const int UP = (U + 3) & ~3;              // slice pitch: every CTA's slice of h is 16-byte aligned
+  const int UP4 = UP >> 2;
   const int u0 = q * U;
   const int b0 = cid * BC;
 
-  // ---- one-time: W_hh slice -> smem (zero padded), h buffers = 0 ---------------------------
+  // ---- one-time: W_hh slice -> smem, h buffers = 0, mbarriers ---------------------------------
+  // hidden index k lives at position (k / U) * UP + (k % U) of the padded h vector; the columns of
+  // the W_hh slice are permuted the same way (padding columns are zero).
   for (int idx = tid; idx < 3 * ULOC * KP; idx += GRU_THREADS) {
-    const int row = idx / KP, k = idx - row * KP;
+    const int row = idx / KP, kp = idx - row * KP;
     const int lu = row / 3, gate = row - lu * 3;
     const int u = u0 + lu;
+    const int src_cta = kp / UP, src_lu = kp - src_cta * UP;
+    const int k = src_cta * U + src_lu;
     float v = 0.f;
-    if (lu < U && u < N && k < N) v = __ldg(a.w_hh + ((long long)gate * N + u) * N + k);
+    if (lu < U && u < N && src_cta < CS && src_lu < U && k < N)
+      v = __ldg(a.w_hh + ((long long)gate * N + u) * N + k);
     Wsm[idx] = v;
   }
   for (int idx = tid; idx < 2 * BC * KP; idx += GRU_THREADS) hbuf[idx] = 0.f;
+  for (int idx = tid; idx < 5 * BC * 32; idx += GRU_THREADS) stage[idx] = 0.f;
+  if (tid == 0) {
+    mbar_init_(&hbar[0], 1);
+    mbar_init_(&hbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tx_bytes = (uint32_t)(CS * BC * UP * sizeof(float));   // bytes every CTA receives per step
 
   // finalising lanes: lane t < UPW*BC owns (local unit w*UPW + t/BC, sequence t%BC)
   const int fi = lane / BC, fb = lane - fi * BC;
@@ -158,6 +213,9 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
 
   for (int s = 0; s < N; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
+    // arm the barrier of the buffer that will receive h_s, then wait until h_{s-1} has fully landed
+    if (tid == 0 && s + 1 < N) mbar_expect_tx_(&hbar[nxt], tx_bytes);
+    if (s > 0) mbar_wait_cluster_(&hbar[cur], (uint32_t)((s - 1) >> 1) & 1u);
     float nx_r = 0.f, nx_z = 0.f, nx_n = 0.f, nx_wk = 0.f, nx_wq = 0.f;
     if (s + 1 < N) {
       load_gi(s + 1, nx_r, nx_z, nx_n);
@@ -206,7 +264,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
         const float gh_r = wsum[(3 * fi + 0) * BC + fb];
         const float gh_z = wsum[(3 * fi + 1) * BC + fb];
         const float gh_n = wsum[(3 * fi + 2) * BC + fb];
-        const float hprev = hbuf[(cur * BC + fb) * KP + u];
+        const float hprev = hbuf[(cur * BC + fb) * KP + q * UP + lu];
         const float r = sigmoidf_(gi_r + gh_r + bhr);
         const float zt = sigmoidf_(gi_z + gh_z + bhz);
         const float nt = tanhf(gi_n + r * (gh_n + bhn));
@@ -223,14 +281,17 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
       stage[fb * 32 + lu] = hn;
     }
     __syncthreads();
-    // (e) scatter the CTA's new slice into every cluster CTA's next buffer (DSMEM)
-    if (lane < U && (u0 + lane) < N) {
-#pragma unroll
-      for (int d = w; d < CS; d += GRU_WARPS) {
-        float* remote = cluster.map_shared_rank(hbuf, d);
-#pragma unroll
-        for (int bb = 0; bb < BC; ++bb)
-          remote[(nxt * BC + bb) * KP + u0 + lane] = stage[bb * 32 + lane];
+    // (e) send the CTA's new slice to every cluster CTA's next buffer: 16-byte st.async stores through
+    //     DSMEM, each signalling the destination's mbarrier (no cluster-wide barrier on the critical path)
+    if (s + 1 < N) {
+      const uint32_t bar_local = smem_addr_u32(&hbar[nxt]);
+      for (int idx = tid; idx < CS * BC * UP4; idx += GRU_THREADS) {
+        const int dest = idx / (BC * UP4);
+        const int rem = idx - dest * (BC * UP4);
+        const int bb = rem / UP4, i4 = rem - bb * UP4;
+        const float4 v = *reinterpret_cast<const float4*>(stage + bb * 32 + 4 * i4);
+        const uint32_t dst_local = smem_addr_u32(hbuf + (nxt * BC + bb) * KP + q * UP + 4 * i4);
+        st_async_v4(map_to_cta(dst_local, (uint32_t)dest), v, map_to_cta(bar_local, (uint32_t)dest));
       }
     }
     if (a.h_all != nullptr && w < BC && (b0 + w) < B && lane < U && (u0 + lane) < N) {
@@ -243,12 +304,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
         a.g_hn[o] = stage[(4 * BC + w) * 32 + lane];
       }
     }
-    // (f) one cluster barrier per step: all slices of h_s are visible before step s+1 reads them
-    __syncwarp();
-    cluster_arrive_release();
     gi_r = nx_r; gi_z = nx_z; gi_n = nx_n; wk_s = nx_wk; wq_s = nx_wq;
-    cluster_wait_acquire();
+    __syncthreads();   // stage[] is rewritten by the next step's gate phase
   }
+  cluster.sync();      // no CTA may exit while peers could still address its shared memory
 
   if (fin && bvalid) {
     a.key[(long long)(b0 + fb) * N + u] = key_acc;
@@ -262,7 +321,7 @@ static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, int* max_active
   constexpr int KP = 128 * JC;
   constexpr int ULOC = GRU_WARPS * UPW;
   const size_t smem =
-      (size_t)(3 * ULOC * KP + 2 * BC * KP + 5 * BC * 32 + GRU_WARPS * 3 * UPW * BC) * sizeof(float);
+      (size_t)(3 * ULOC * KP + 2 * BC * KP + 5 * BC * 32 + GRU_WARPS * 3 * UPW * BC) * sizeof(float) + 16;
   auto kern = gru_cluster_kernel<JC, UPW, CS, BC>;
   static bool attr_set = false;   // one process drives one device (DDP = process per GPU)
   static int max_clusters = 0;
@@ -306,7 +365,7 @@ template <int CS, int BC>
 static int dispatch_gru_cluster(const GruArgs& a, cudaStream_t st, int* probe) {
   const int U = ceil_div(a.N, CS);
   const int upw = ceil_div(U, GRU_WARPS);
-  const int jc = ceil_div(a.N, 128);
+  const int jc = ceil_div(CS * ((U + 3) & ~3), 128);     // padded h vector: CS slices of pitch round4(U)
   if (upw > 4 || jc > 4) return -1;
 #define SG_GRU_CASE(J, P) \
   if (jc == J && upw == P) return launch_gru_cluster<J, P, CS, BC>(a, st, probe);
