@@ -102,6 +102,9 @@ typedef struct {
   const uint8_t* dropout_mask; /* optional explicit keep-mask (B,N,N) of {0,1}; overrides Philox */
   int gemm_mode;            /* 0 = auto (tcgen05 TF32 for the GLU chain when available),
                                1 = force fp32 FFMA everywhere, 2 = force tcgen05 TF32 */
+  int reuse_folded;         /* 1: the DFT-folded weights already in `workspace` (written by an earlier
+                               forward with the SAME parameter values) are reused instead of being
+                               recomputed — for inference loops with frozen weights */
 } stemgnn_fwd_opts_t;
 
 /* ---- library ------------------------------------------------------------------------ */

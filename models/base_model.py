@@ -58,6 +58,9 @@ class StockBlockLayer(nn.Module):
         self.backcast_short_cut = nn.Linear(time_step, time_step)
         self.output_channel = 4 * multi_layer
         d = time_step * self.output_channel
+        # stage-level calls (spe_seq_cell / forward of a single block) default to exact fp32 GEMMs;
+        # the fused Model.forward path uses the tcgen05 TF32 GLU chain (Model.gemm_mode)
+        self.gemm_mode = runtime.GEMM_FP32
         self.GLUs = nn.ModuleList()
         for fan_in in (4 * time_step, d, d):
             self.GLUs.append(GLU(fan_in, d))    # real chain  (even index)
@@ -85,7 +88,7 @@ class StockBlockLayer(nn.Module):
         out = torch.empty(B, 4, N, W * self.multi, device=g.device)
         bp = self._block_ptrs()
         rc = _lib.load().stemgnn_spe_seq_cell_forward(
-            ctypes.byref(dims), ctypes.byref(bp), runtime.GEMM_AUTO, g.data_ptr(), out.data_ptr(),
+            ctypes.byref(dims), ctypes.byref(bp), self.gemm_mode, g.data_ptr(), out.data_ptr(),
             ws.data_ptr(), ws.numel(), runtime._stream_ptr(g.device))
         _lib.check(rc, "stemgnn_spe_seq_cell_forward")
         return out
@@ -103,7 +106,7 @@ class StockBlockLayer(nn.Module):
         backcast = torch.empty(B, N, W, device=xb.device) if self.stack_cnt == 0 else None
         bp = self._block_ptrs()
         rc = _lib.load().stemgnn_block_forward(
-            ctypes.byref(dims), ctypes.byref(bp), self.stack_cnt, runtime.GEMM_AUTO, xb.data_ptr(),
+            ctypes.byref(dims), ctypes.byref(bp), self.stack_cnt, self.gemm_mode, xb.data_ptr(),
             mul_L.data_ptr(), forecast.data_ptr(), backcast.data_ptr() if backcast is not None else None,
             ws.data_ptr(), ws.numel(), runtime._stream_ptr(xb.device))
         _lib.check(rc, "stemgnn_block_forward")
@@ -194,10 +197,14 @@ class Model(nn.Module):
         dims = self._dims(x.shape[0])
         key = (x.shape[0], x.device)
         ws = rt["ws"].get(key)
+        # the DFT-folded weights inside the workspace stay valid while no parameter was written to
+        versions = tuple(p._version for p in rt["params"])
+        reuse = ws is not None and rt.get("folded_for") == (key, versions, self.gemm_mode)
         if ws is None:
             rt["ws"].clear()
             ws = rt["ws"][key] = runtime.alloc_workspace(dims, False, x.device)
-        opts = runtime.make_opts(self.alpha, 0.0, False, gemm_mode=self.gemm_mode)
+        rt["folded_for"] = (key, versions, self.gemm_mode)
+        opts = runtime.make_opts(self.alpha, 0.0, False, gemm_mode=self.gemm_mode, reuse_folded=reuse)
         return runtime.model_forward_raw(dims, rt["ptrs"], opts, x, ws, want_mul_L)
 
     def forward(self, x, dropout_mask=None):

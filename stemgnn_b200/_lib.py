@@ -34,7 +34,7 @@ class ModelPtrs(Structure):
 class FwdOpts(Structure):
     _fields_ = [("leaky_alpha", c_float), ("dropout_p", c_float), ("training", c_int),
                 ("dropout_seed", c_uint64), ("dropout_offset", c_uint64), ("dropout_mask", c_void_p),
-                ("gemm_mode", c_int)]
+                ("gemm_mode", c_int), ("reuse_folded", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/stemgnn_b200.h declares

@@ -170,11 +170,11 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
 
 // StockBlockLayer.forward (base_model.py:61-75)
 int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int stack_idx,
-                  int gemm_mode, const float* x_bnw, const float* x_bwn, const float* mul_L,
-                  const BlockWs& b, cudaStream_t st) {
+                  int gemm_mode, int reuse_folded, const float* x_bnw, const float* x_bwn,
+                  const float* mul_L, const BlockWs& b, cudaStream_t st) {
   const int B = dm.B, N = dm.N, W = dm.W, T = dm.multi * W, d = 4 * T, R = B * N;
   const int PW = (stack_idx == 0) ? T + W : T;
-  SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
+  if (!reuse_folded) SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
   SG_TRY(launch_gft(mul_L, x_bwn, b.G, B, N, W, st));
   SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st));
   {
@@ -284,9 +284,10 @@ int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
                 p->weight_query, ws.key, ws.query, ws.h_all, ws.gi, ws.g_r, ws.g_z, ws.g_n, ws.g_hn, dm.B, dm.N, dm.W};
   SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
   SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
-  SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, ws.x_bnw, x, ws.mul_L, ws.blk[0], st));
-  SG_TRY(block_forward(dm, p->block[1], 1, opts->gemm_mode, ws.blk[0].bc_bnw, ws.blk[0].bc_bwn,
-                       ws.mul_L, ws.blk[1], st));
+  SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, opts->reuse_folded && !opts->training, ws.x_bnw, x,
+                       ws.mul_L, ws.blk[0], st));
+  SG_TRY(block_forward(dm, p->block[1], 1, opts->gemm_mode, opts->reuse_folded && !opts->training,
+                       ws.blk[0].bc_bnw, ws.blk[0].bc_bwn, ws.mul_L, ws.blk[1], st));
   SG_TRY(launch_model_head(ws.blk[0].forecast, ws.blk[1].forecast, p->fc0_w, p->fc0_b, p->fc2_w,
                            p->fc2_b, forecast, dm.B, dm.N, dm.W, dm.H, st));
   if (mul_L != nullptr)
@@ -356,7 +357,7 @@ int stemgnn_block_forward(const stemgnn_dims_t* dims, const stemgnn_block_params
   float* x_bwn = ws.blk[1 - stack_idx].bc_bwn;   // scratch from the other block's slot
   bnw_to_bwn_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x_bnw, x_bwn, dims->B, dims->N, dims->W);
   SG_LAUNCH_CHECK("bnw_to_bwn_kernel");
-  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, x_bnw, x_bwn, mul_L, b, st));
+  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, 0, x_bnw, x_bwn, mul_L, b, st));
   SG_CUDA(cudaMemcpyAsync(forecast, b.forecast, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (stack_idx == 0)
     SG_CUDA(cudaMemcpyAsync(backcast, b.bc_bnw, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -66,7 +66,7 @@ __device__ __forceinline__ void mbar_wait_cluster_(uint64_t* bar, uint32_t parit
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
@@ -177,6 +177,24 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tx_bytes = (uint32_t)(CS * BC * UP * sizeof(float));   // bytes every CTA receives per step
+  // step-invariant send descriptors: item -> (float4 in stage[], remote destination, remote mbarrier)
+  constexpr int SEND_ITEMS = (CS * BC * 8 + GRU_THREADS - 1) / GRU_THREADS;   // UP4 <= 8
+  int snd_src[SEND_ITEMS];
+  uint32_t snd_dst[SEND_ITEMS], snd_bar[SEND_ITEMS];
+#pragma unroll
+  for (int it = 0; it < SEND_ITEMS; ++it) {
+    const int idx = tid + it * GRU_THREADS;
+    snd_src[it] = -1;
+    snd_dst[it] = snd_bar[it] = 0;
+    if (idx < CS * BC * UP4) {
+      const int dest = idx / (BC * UP4);
+      const int rem = idx - dest * (BC * UP4);
+      const int bb = rem / UP4, i4 = rem - bb * UP4;
+      snd_src[it] = bb * 32 + 4 * i4;
+      snd_dst[it] = map_to_cta(smem_addr_u32(hbuf + bb * KP + q * UP + 4 * i4), (uint32_t)dest);
+      snd_bar[it] = map_to_cta(smem_addr_u32(&hbar[0]), (uint32_t)dest);
+    }
+  }
 
   // finalising lanes: lane t < UPW*BC owns (local unit w*UPW + t/BC, sequence t%BC)
   const int fi = lane / BC, fb = lane - fi * BC;
@@ -284,14 +302,12 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
     // (e) send the CTA's new slice to every cluster CTA's next buffer: 16-byte st.async stores through
     //     DSMEM, each signalling the destination's mbarrier (no cluster-wide barrier on the critical path)
     if (s + 1 < N) {
-      const uint32_t bar_local = smem_addr_u32(&hbar[nxt]);
-      for (int idx = tid; idx < CS * BC * UP4; idx += GRU_THREADS) {
-        const int dest = idx / (BC * UP4);
-        const int rem = idx - dest * (BC * UP4);
-        const int bb = rem / UP4, i4 = rem - bb * UP4;
-        const float4 v = *reinterpret_cast<const float4*>(stage + bb * 32 + 4 * i4);
-        const uint32_t dst_local = smem_addr_u32(hbuf + (nxt * BC + bb) * KP + q * UP + 4 * i4);
-        st_async_v4(map_to_cta(dst_local, (uint32_t)dest), v, map_to_cta(bar_local, (uint32_t)dest));
+#pragma unroll
+      for (int it = 0; it < SEND_ITEMS; ++it) {
+        if (snd_src[it] >= 0) {
+          const float4 v = *reinterpret_cast<const float4*>(stage + snd_src[it]);
+          st_async_v4(snd_dst[it] + (uint32_t)nxt * (BC * KP * 4), v, snd_bar[it] + (uint32_t)nxt * 8);
+        }
       }
     }
     if (a.h_all != nullptr && w < BC && (b0 + w) < B && lane < U && (u0 + lane) < N) {

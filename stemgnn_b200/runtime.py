@@ -98,7 +98,7 @@ def alloc_workspace(dims, training, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
-def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AUTO):
+def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AUTO, reuse_folded=False):
     o = FwdOpts()
     o.leaky_alpha = float(alpha)
     o.dropout_p = float(p)
@@ -107,6 +107,7 @@ def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AU
     o.dropout_offset = int(offset) & 0xFFFFFFFFFFFFFFFF
     o.dropout_mask = mask.data_ptr() if mask is not None else None
     o.gemm_mode = int(gemm_mode)
+    o.reuse_folded = int(bool(reuse_folded))
     return o
 
 

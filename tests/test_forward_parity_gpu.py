@@ -285,3 +285,23 @@ def test_cpu_tensor_is_rejected_loudly():
     x, _ = tp.synthetic_batch(c["B"], c["N"], c["W"], c["H"])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(x)
+
+
+def test_folded_weight_cache_is_invalidated_by_parameter_updates():
+    """Eval forwards reuse the DFT-folded weights in the workspace until a parameter changes."""
+    c = cases("forward")["tiny_taps"]
+    m = build_model(c, DEV).eval()
+    x, _ = tp.synthetic_batch(c["B"], c["N"], c["W"], c["H"], seed=1234)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        f1, _ = m(xd)
+        f2, _ = m(xd)                                   # cached folds
+        assert torch.equal(f1, f2)
+        m.stock_block[0].GLUs[0].linear_left.weight.mul_(1.5)      # touches a folded weight
+        m.stock_block[1].weight.add_(0.01)                          # touches the output fold
+        f3, _ = m(xd)
+    p = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        f_ref, _ = tp.model_forward(x, p)
+    assert not torch.equal(f1, f3)
+    assert_close(f3, f_ref, msg="forward after in-place weight update")

@@ -63,3 +63,26 @@ def test_model_forward_tensor_core_path_vs_reference_golden(name):
     assert_close(forecast, g["forecast"], msg=name + " forecast (tcgen05 TF32 GLU chain)")
     err = np.abs(forecast.cpu().numpy() - g["forecast"])
     print(f"{name}: forecast max|err| = {err.max():.2e}, MAE vs reference = {err.mean():.2e}")
+
+
+def test_stage_level_block_on_tensor_cores_has_tf32_error_only():
+    """Stage-level StockBlockLayer on the tcgen05 path: iffted carries TF32-level error (documented in
+    DESIGN.md §6), the block outputs (after the sigmoid heads) stay within the fp32 tolerance."""
+    from stemgnn_b200 import runtime
+    c = cases("forward")["tiny_taps"]
+    g = golden("tiny_taps")
+    m = build_model(c, DEV).eval()
+    x, _ = tp.synthetic_batch(c["B"], c["N"], c["W"], c["H"], seed=1234)
+    mul_L = torch.from_numpy(g["mul_L"]).to(DEV)
+    X = x.permute(0, 2, 1).contiguous().unsqueeze(1).to(DEV)
+    blk = m.stock_block[0]
+    blk.gemm_mode = runtime.GEMM_TC
+    gfted = torch.matmul(mul_L.unsqueeze(1).cpu(), X.unsqueeze(1).cpu()).to(DEV)
+    iff = blk.spe_seq_cell(gfted)
+    err = (iff.cpu() - torch.from_numpy(g["block0.iffted"])).abs().max().item()
+    scale = float(np.abs(g["block0.iffted"]).max())
+    print(f"iffted TF32 stage error: {err:.2e} (max |iffted| = {scale:.2e})")
+    assert err < 5e-3 * max(scale, 1.0)
+    fc, back = blk(X, mul_L)
+    assert_close(fc, g["block0.forecast"], msg="block0.forecast on tensor cores")
+    assert_close(back, g["block0.backcast"], msg="block0.backcast on tensor cores")
