@@ -17,6 +17,7 @@ Prints ONE JSON line.  Keys (see the task contract):
   cpu_baseline          oracle/torch_port.py (the reference's ATen op sequence) on the host cores
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -198,6 +199,33 @@ def run_ours(args, rank, world, local_rank):
             gru_ms = None
             sys.stderr.write(f"[bench] GRU event hook failed: {exc}\n")
 
+        # ---- the tcgen05 GLU layer (61 % of the flops), timed alone through the C ABI with CUDA events ----
+        glu_ms = None
+        try:
+            R, d = B * N, 4 * MULTI * W
+            ga = torch.randn(R, d, device=dev)
+            gw = [torch.randn(d, d, device=dev) / d ** 0.5 for _ in range(2)]
+            gb = [torch.zeros(d, device=dev) for _ in range(2)]
+            go = torch.empty(R, d, device=dev)
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+            def glu_call():
+                rc = lib.stemgnn_glu_gemm(R, d, d, ga.data_ptr(), d, gw[0].data_ptr(), gb[0].data_ptr(),
+                                          gw[1].data_ptr(), gb[1].data_ptr(), go.data_ptr(), d, 1, st)
+                if rc:
+                    raise RuntimeError(lib.stemgnn_last_error().decode())
+            for _ in range(3):
+                glu_call()
+            tot, reps = 0.0, 10
+            for _ in range(reps):
+                flush.zero_()
+                e0.record(); glu_call(); e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            glu_ms = tot / reps
+        except Exception as exc:
+            sys.stderr.write(f"[bench] GLU kernel timing failed: {exc}\n")
+
         # ---- end to end through the public API with host buffers ----------------------------------
         out_host = torch.empty(B, H, N).pin_memory()
         for _ in range(3):
@@ -281,6 +309,13 @@ def run_ours(args, rank, world, local_rank):
                               + (" + flat-gradient NCCL all-reduce" if world > 1 else "") + " + RMSprop step"},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "roofline_glu": None if not glu_ms else {
+                "kernel": "glu_tc_kernel (tcgen05 kind::tf32, one 240->240 GLU layer over B*N=11456 rows)",
+                "bound": "tensor", "achieved": 4.0 * B * N * 240 * 240 / (glu_ms * 1e-3) / 1e12,
+                "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": 4.0 * B * N * 240 * 240 / (glu_ms * 1e-3) / 1e12 / peak_tf,
+                "ms_per_launch": glu_ms, "peak_source": peak_src + " (bf16 figure; TF32 runs at half rate)",
+                "note": "L2 flushed before each launch: weights and activations come from HBM"},
             "cpu_baseline": {"value": cpu_v, "unit": "windows/s", "cores": threads, "kind": "port",
                              "sample": f"{cpu_steps} eval forwards of one {B}-window batch "
                                        f"({cpu_ms:.1f} ms each); os.cpu_count()={os.cpu_count()}"},

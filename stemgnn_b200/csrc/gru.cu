@@ -4,7 +4,7 @@
 // The recurrence is N dependent steps of h(B x N) . W_hh^T(N x 3N): latency-bound, O(B N^3).
 // B200 design (DESIGN.md "GRU"):
 //   * batch elements are independent sequences -> one THREAD-BLOCK CLUSTER of CS=16 CTAs per
-//     group of 4 batch elements (8 clusters = 128 SMs at B=32);
+//     4-5 sequences (7 clusters x 5 sequences = 112 SMs at B=32);
 //   * each CTA of a cluster owns ceil(N/16) hidden units: its 3*U rows of W_hh stay resident in
 //     shared memory for all N steps (persistent-RNN), so W_hh is read from HBM exactly once;
 //   * per step: packed-fp32 (FFMA2) mat-vec against the 4 hidden vectors, gate math, then the new
@@ -17,6 +17,7 @@
 //     output is never materialised in eval mode (it is written only when the backward needs it).
 // A generic per-step-launch path covers N > 512 or devices that refuse the 16-CTA cluster.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -128,21 +129,28 @@ __device__ __forceinline__ void warp_reduce_to_smem(const float* vals, float* ou
   }
 }
 
-// JC: K padded to 128*JC;  UPW: hidden units per warp;  CS: cluster size;  BC: sequences per cluster
-template <int JC, int UPW, int CS, int BC>
+// Fast gate nonlinearities (ex2.approx + approximate division: ~2 ulp, abs error < 3e-7 on the gates)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 2.0f * fast_sigmoid(2.0f * x) - 1.0f; }
+
+// JC: padded h length = 128*JC;  UPW: hidden units per warp;  CS: cluster size;
+// NG x G: a cluster owns NG independent groups of G sequences.  With NG = 2 the groups are software
+// pipelined: while group A's new hidden slices travel through DSMEM, the CTA computes group B.
+template <int JC, int UPW, int CS, int NG, int G>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) {
   constexpr int KP = 128 * JC;
   constexpr int ULOC = GRU_WARPS * UPW;     // padded units per CTA
   constexpr int ROWS = 3 * UPW;             // W_hh rows per warp
-  constexpr int V = ROWS * BC;              // dot products per warp per step
-  static_assert(UPW * BC <= 32, "finalising lanes");
+  constexpr int V = ROWS * G;               // dot products per warp per group-step
+  constexpr int BC = NG * G;                // sequences per cluster
+  static_assert(UPW * G <= 32, "finalising lanes");
 
   extern __shared__ __align__(16) float smem[];
   float* Wsm = smem;                              // [3*ULOC][KP]
-  float* hbuf = Wsm + 3 * ULOC * KP;              // [2][BC][KP]
-  float* stage = hbuf + 2 * BC * KP;              // [5][BC][32]: new h, and (training) r, z, n, hn
-  float* sums = stage + 5 * BC * 32;              // [WARPS][V]
-  uint64_t* hbar = reinterpret_cast<uint64_t*>(sums + GRU_WARPS * V);   // [2] one mbarrier per h buffer
+  float* hbuf = Wsm + 3 * ULOC * KP;              // [NG][2][G][KP]
+  float* stage = hbuf + NG * 2 * G * KP;          // [NG][5][G][32]: new h, and (training) r, z, n, hn
+  float* sums = stage + NG * 5 * G * 32;          // [WARPS][V]
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(sums + GRU_WARPS * V + ((GRU_WARPS * V) & 1));   // [NG][2]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
@@ -169,16 +177,18 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
       v = __ldg(a.w_hh + ((long long)gate * N + u) * N + k);
     Wsm[idx] = v;
   }
-  for (int idx = tid; idx < 2 * BC * KP; idx += GRU_THREADS) hbuf[idx] = 0.f;
-  for (int idx = tid; idx < 5 * BC * 32; idx += GRU_THREADS) stage[idx] = 0.f;
+  for (int idx = tid; idx < NG * 2 * G * KP; idx += GRU_THREADS) hbuf[idx] = 0.f;
+  for (int idx = tid; idx < NG * 5 * G * 32; idx += GRU_THREADS) stage[idx] = 0.f;
   if (tid == 0) {
-    mbar_init_(&hbar[0], 1);
-    mbar_init_(&hbar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NG * 2; ++i) mbar_init_(&hbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t tx_bytes = (uint32_t)(CS * BC * UP * sizeof(float));   // bytes every CTA receives per step
-  // step-invariant send descriptors: item -> (float4 in stage[], remote destination, remote mbarrier)
-  constexpr int SEND_ITEMS = (CS * BC * 8 + GRU_THREADS - 1) / GRU_THREADS;   // UP4 <= 8
+  const uint32_t tx_bytes = (uint32_t)(CS * G * UP * sizeof(float));   // bytes a CTA receives per group-step
+
+  // step-invariant send descriptors (same for every group up to a constant offset):
+  // item -> (float4 inside stage[g][0], remote destination inside hbuf[g][0], remote mbarrier hbar[g][0])
+  constexpr int SEND_ITEMS = (CS * G * 8 + GRU_THREADS - 1) / GRU_THREADS;   // UP4 <= 8
   int snd_src[SEND_ITEMS];
   uint32_t snd_dst[SEND_ITEMS], snd_bar[SEND_ITEMS];
 #pragma unroll
@@ -186,9 +196,9 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
     const int idx = tid + it * GRU_THREADS;
     snd_src[it] = -1;
     snd_dst[it] = snd_bar[it] = 0;
-    if (idx < CS * BC * UP4) {
-      const int dest = idx / (BC * UP4);
-      const int rem = idx - dest * (BC * UP4);
+    if (idx < CS * G * UP4) {
+      const int dest = idx / (G * UP4);
+      const int rem = idx - dest * (G * UP4);
       const int bb = rem / UP4, i4 = rem - bb * UP4;
       snd_src[it] = bb * 32 + 4 * i4;
       snd_dst[it] = map_to_cta(smem_addr_u32(hbuf + bb * KP + q * UP + 4 * i4), (uint32_t)dest);
@@ -196,152 +206,176 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
     }
   }
 
-  // finalising lanes: lane t < UPW*BC owns (local unit w*UPW + t/BC, sequence t%BC)
-  const int fi = lane / BC, fb = lane - fi * BC;
+  // finalising lanes: lane t < UPW*G owns (local unit w*UPW + t/G, sequence t%G of each group)
+  const int fi = lane / G, fb = lane - fi * G;
   const int lu = w * UPW + fi;
   const int u = u0 + lu;
-  const bool flane = lane < UPW * BC;
+  const bool flane = lane < UPW * G;
   const bool fin = flane && (lu < U) && (u < N);
-  const bool bvalid = (b0 + fb) < B;
   float bhr = 0.f, bhz = 0.f, bhn = 0.f;
   if (fin) {
     bhr = __ldg(a.b_hh + u);
     bhz = __ldg(a.b_hh + N + u);
     bhn = __ldg(a.b_hh + 2 * N + u);
   }
-  float key_acc = 0.f, query_acc = 0.f;
+  float key_acc[NG], query_acc[NG], gi_r[NG], gi_z[NG], gi_n[NG];
+  bool bvalid[NG];
 
   // input projection W_i{r,z,n} x_s + b_i{r,z,n} comes precomputed (gru_input_proj); the values of
-  // step s+1 are requested at the top of step s so their latency hides behind the mat-vec.
-  auto load_gi = [&](int s, float& gr, float& gz, float& gn) {
+  // step s+1 are requested while step s computes so their latency hides behind the mat-vec.
+  auto load_gi = [&](int s, int bglob, bool ok, float& gr, float& gz, float& gn) {
     gr = gz = gn = 0.f;
-    if (fin && bvalid) {
-      const float* g = a.gi + ((long long)s * B + (b0 + fb)) * (3 * N) + u;
+    if (fin && ok) {
+      const float* g = a.gi + ((long long)s * B + bglob) * (3 * N) + u;
       gr = __ldg(g);
       gz = __ldg(g + N);
       gn = __ldg(g + 2 * N);
     }
   };
-  float gi_r, gi_z, gi_n;
-  load_gi(0, gi_r, gi_z, gi_n);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    key_acc[g] = query_acc[g] = 0.f;
+    bvalid[g] = (b0 + g * G + fb) < B;
+    load_gi(0, b0 + g * G + fb, bvalid[g], gi_r[g], gi_z[g], gi_n[g]);
+  }
   float wk_s = __ldg(a.wk + 0), wq_s = __ldg(a.wq + 0);
 
   __syncthreads();
-  cluster.sync();   // every CTA's buffers are initialised before any remote write
+  cluster.sync();   // every CTA's buffers and barriers are initialised before any remote write
 
   for (int s = 0; s < N; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
-    // arm the barrier of the buffer that will receive h_s, then wait until h_{s-1} has fully landed
-    if (tid == 0 && s + 1 < N) mbar_expect_tx_(&hbar[nxt], tx_bytes);
-    if (s > 0) mbar_wait_cluster_(&hbar[cur], (uint32_t)((s - 1) >> 1) & 1u);
-    float nx_r = 0.f, nx_z = 0.f, nx_n = 0.f, nx_wk = 0.f, nx_wq = 0.f;
+    float nx_wk = 0.f, nx_wq = 0.f;
     if (s + 1 < N) {
-      load_gi(s + 1, nx_r, nx_z, nx_n);
       nx_wk = __ldg(a.wk + s + 1);
       nx_wq = __ldg(a.wq + s + 1);
     }
-    // (a) this lane's k-slice of h_{s-1} for all BC sequences: k = 128*j + 4*lane + {0..3}
-    float4 h[BC][JC];
 #pragma unroll
-    for (int bb = 0; bb < BC; ++bb)
-#pragma unroll
-      for (int j = 0; j < JC; ++j)
-        h[bb][j] = *reinterpret_cast<const float4*>(hbuf + (cur * BC + bb) * KP + 128 * j + 4 * lane);
+    for (int g = 0; g < NG; ++g) {
+      float* hb_cur = hbuf + ((g * 2 + cur) * G) * KP;
+      float* stg = stage + g * 5 * G * 32;
+      // arm the barrier of the buffer that will receive h_s, wait until h_{s-1} of this group landed
+      if (tid == 0 && s + 1 < N) mbar_expect_tx_(&hbar[g * 2 + nxt], tx_bytes * (uint32_t)a.xrep);
+      if (s > 0) mbar_wait_cluster_(&hbar[g * 2 + cur], (uint32_t)((s - 1) >> 1) & 1u);
+      float nx_r = 0.f, nx_z = 0.f, nx_n = 0.f;
+      if (s + 1 < N) load_gi(s + 1, b0 + g * G + fb, bvalid[g], nx_r, nx_z, nx_n);
 
-    // (b) mat-vec: each W_hh element is read from shared memory exactly once per step (32 lanes x 16 B
-    //     distinct per LDS.128) and used for all BC sequences; two partial sums per (row, sequence).
-    float2 acc[ROWS][BC];
-    const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * lane;
+      // (a) this lane's k-slice of h_{s-1} for the G sequences: k' = 128*j + 4*lane + {0..3}
+      float4 h[G][JC];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
+      for (int bb = 0; bb < G; ++bb)
 #pragma unroll
-      for (int bb = 0; bb < BC; ++bb) acc[r][bb] = make_float2(0.f, 0.f);
+        for (int j = 0; j < JC; ++j)
+          h[bb][j] = *reinterpret_cast<const float4*>(hb_cur + bb * KP + 128 * j + 4 * lane);
+
+      // (b) mat-vec: each W_hh element is read from shared memory once per group-step (32 lanes x 16 B
+      //     distinct per LDS.128) and used for the G sequences; two partial sums per (row, sequence)
+      float2 acc[ROWS][G];
+      const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * lane;
 #pragma unroll
-      for (int j = 0; j < JC; ++j) {
-        const float4 wv = *reinterpret_cast<const float4*>(wbase + r * KP + 128 * j);
+      for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-        for (int bb = 0; bb < BC; ++bb) {
-          acc[r][bb] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[bb][j].x, h[bb][j].y), acc[r][bb]);
-          acc[r][bb] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[bb][j].z, h[bb][j].w), acc[r][bb]);
+        for (int bb = 0; bb < G; ++bb) acc[r][bb] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < JC; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(wbase + r * KP + 128 * j);
+#pragma unroll
+          for (int bb = 0; bb < G; ++bb) {
+            acc[r][bb] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[bb][j].x, h[bb][j].y), acc[r][bb]);
+            acc[r][bb] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[bb][j].z, h[bb][j].w), acc[r][bb]);
+          }
         }
       }
-    }
-    // (c) reduce the V partial dot products over the 32 lanes (recursive halving) -> sums[w][V]
-    float part[V];
+      // (c) reduce the V partial dot products over the 32 lanes (recursive halving) -> sums[w][V]
+      float part[V];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
+      for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-      for (int bb = 0; bb < BC; ++bb) part[r * BC + bb] = acc[r][bb].x + acc[r][bb].y;
-    float* wsum = sums + w * V;
-    warp_reduce_to_smem<V>(part, wsum, lane);
-    __syncwarp();
-    // (d) gates for (unit, sequence) on the first UPW*BC lanes
-    if (flane) {
-      float hn = 0.f;
-      if (fin) {
-        const float gh_r = wsum[(3 * fi + 0) * BC + fb];
-        const float gh_z = wsum[(3 * fi + 1) * BC + fb];
-        const float gh_n = wsum[(3 * fi + 2) * BC + fb];
-        const float hprev = hbuf[(cur * BC + fb) * KP + q * UP + lu];
-        const float r = sigmoidf_(gi_r + gh_r + bhr);
-        const float zt = sigmoidf_(gi_z + gh_z + bhz);
-        const float nt = tanhf(gi_n + r * (gh_n + bhn));
-        hn = (1.f - zt) * nt + zt * hprev;
-        key_acc = fmaf(hn, wk_s, key_acc);
-        query_acc = fmaf(hn, wq_s, query_acc);
-        if (a.g_r != nullptr) {   // gate values for BPTT
-          stage[(1 * BC + fb) * 32 + lu] = r;
-          stage[(2 * BC + fb) * 32 + lu] = zt;
-          stage[(3 * BC + fb) * 32 + lu] = nt;
-          stage[(4 * BC + fb) * 32 + lu] = gh_n + bhn;
+        for (int bb = 0; bb < G; ++bb) part[r * G + bb] = acc[r][bb].x + acc[r][bb].y;
+      float* wsum = sums + w * V;
+      warp_reduce_to_smem<V>(part, wsum, lane);
+      __syncwarp();
+      // (d) gates for (unit, sequence) on the first UPW*G lanes
+      if (flane) {
+        float hn = 0.f;
+        if (fin) {
+          const float gh_r = wsum[(3 * fi + 0) * G + fb];
+          const float gh_z = wsum[(3 * fi + 1) * G + fb];
+          const float gh_n = wsum[(3 * fi + 2) * G + fb];
+          const float hprev = hb_cur[fb * KP + q * UP + lu];
+          const float r = fast_sigmoid(gi_r[g] + gh_r + bhr);
+          const float zt = fast_sigmoid(gi_z[g] + gh_z + bhz);
+          const float nt = fast_tanh(gi_n[g] + r * (gh_n + bhn));
+          hn = (1.f - zt) * nt + zt * hprev;
+          key_acc[g] = fmaf(hn, wk_s, key_acc[g]);
+          query_acc[g] = fmaf(hn, wq_s, query_acc[g]);
+          if (a.g_r != nullptr) {   // gate values for BPTT
+            stg[(1 * G + fb) * 32 + lu] = r;
+            stg[(2 * G + fb) * 32 + lu] = zt;
+            stg[(3 * G + fb) * 32 + lu] = nt;
+            stg[(4 * G + fb) * 32 + lu] = gh_n + bhn;
+          }
+        }
+        stg[fb * 32 + lu] = hn;
+      }
+      __syncthreads();
+      // (e) send the CTA's new slice to every cluster CTA's next buffer: 16-byte st.async stores through
+      //     DSMEM, each signalling the destination's mbarrier (no cluster-wide barrier on the critical path)
+      if (s + 1 < N) {
+        const uint32_t dst_off = (uint32_t)((g * 2 + nxt) * G * KP * 4);
+        const uint32_t bar_off = (uint32_t)((g * 2 + nxt) * 8);
+        for (int rep = 1; rep < a.xrep; ++rep)     // measurement knob only (STEMGNN_GRU_XREP)
+#pragma unroll
+          for (int it = 0; it < SEND_ITEMS; ++it)
+            if (snd_src[it] >= 0)
+              st_async_v4(snd_dst[it] + dst_off, *reinterpret_cast<const float4*>(stg + snd_src[it]),
+                          snd_bar[it] + bar_off);
+#pragma unroll
+        for (int it = 0; it < SEND_ITEMS; ++it) {
+          if (snd_src[it] >= 0) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + snd_src[it]);
+            st_async_v4(snd_dst[it] + dst_off, v, snd_bar[it] + bar_off);
+          }
         }
       }
-      stage[fb * 32 + lu] = hn;
-    }
-    __syncthreads();
-    // (e) send the CTA's new slice to every cluster CTA's next buffer: 16-byte st.async stores through
-    //     DSMEM, each signalling the destination's mbarrier (no cluster-wide barrier on the critical path)
-    if (s + 1 < N) {
-#pragma unroll
-      for (int it = 0; it < SEND_ITEMS; ++it) {
-        if (snd_src[it] >= 0) {
-          const float4 v = *reinterpret_cast<const float4*>(stage + snd_src[it]);
-          st_async_v4(snd_dst[it] + (uint32_t)nxt * (BC * KP * 4), v, snd_bar[it] + (uint32_t)nxt * 8);
+      if (a.h_all != nullptr && w < G && (b0 + g * G + w) < B && lane < U && (u0 + lane) < N) {
+        const long long o = ((long long)s * B + (b0 + g * G + w)) * N + u0 + lane;
+        a.h_all[o] = stg[w * 32 + lane];
+        if (a.g_r != nullptr) {
+          a.g_r[o] = stg[(1 * G + w) * 32 + lane];
+          a.g_z[o] = stg[(2 * G + w) * 32 + lane];
+          a.g_n[o] = stg[(3 * G + w) * 32 + lane];
+          a.g_hn[o] = stg[(4 * G + w) * 32 + lane];
         }
       }
+      gi_r[g] = nx_r; gi_z[g] = nx_z; gi_n[g] = nx_n;
+      if (NG == 1) __syncthreads();   // stage[] is rewritten by the next step's gate phase
     }
-    if (a.h_all != nullptr && w < BC && (b0 + w) < B && lane < U && (u0 + lane) < N) {
-      const long long o = ((long long)s * B + (b0 + w)) * N + u0 + lane;
-      a.h_all[o] = stage[w * 32 + lane];
-      if (a.g_r != nullptr) {
-        a.g_r[o] = stage[(1 * BC + w) * 32 + lane];
-        a.g_z[o] = stage[(2 * BC + w) * 32 + lane];
-        a.g_n[o] = stage[(3 * BC + w) * 32 + lane];
-        a.g_hn[o] = stage[(4 * BC + w) * 32 + lane];
-      }
-    }
-    gi_r = nx_r; gi_z = nx_z; gi_n = nx_n; wk_s = nx_wk; wq_s = nx_wq;
-    __syncthreads();   // stage[] is rewritten by the next step's gate phase
+    wk_s = nx_wk; wq_s = nx_wq;
   }
   cluster.sync();      // no CTA may exit while peers could still address its shared memory
 
-  if (fin && bvalid) {
-    a.key[(long long)(b0 + fb) * N + u] = key_acc;
-    a.query[(long long)(b0 + fb) * N + u] = query_acc;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (fin && bvalid[g]) {
+      a.key[(long long)(b0 + g * G + fb) * N + u] = key_acc[g];
+      a.query[(long long)(b0 + g * G + fb) * N + u] = query_acc[g];
+    }
   }
 }
 
 // returns 0 launched, -1 configuration not launchable here, >0 error
-template <int JC, int UPW, int CS, int BC>
+template <int JC, int UPW, int CS, int NG, int G>
 static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, int* max_active_out) {
   constexpr int KP = 128 * JC;
   constexpr int ULOC = GRU_WARPS * UPW;
-  const size_t smem =
-      (size_t)(3 * ULOC * KP + 2 * BC * KP + 5 * BC * 32 + GRU_WARPS * 3 * UPW * BC) * sizeof(float) + 16;
-  auto kern = gru_cluster_kernel<JC, UPW, CS, BC>;
+  constexpr int V = 3 * UPW * G;
+  const size_t smem = (size_t)(3 * ULOC * KP + NG * 2 * G * KP + NG * 5 * G * 32 + GRU_WARPS * V + 2) * sizeof(float) +
+                      NG * 2 * sizeof(uint64_t);
+  auto kern = gru_cluster_kernel<JC, UPW, CS, NG, G>;
   static bool attr_set = false;   // one process drives one device (DDP = process per GPU)
   static int max_clusters = 0;
-  const int nclusters = ceil_div(a.B, BC);
+  const int nclusters = ceil_div(a.B, NG * G);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
   cfg.blockDim = dim3(GRU_THREADS);
@@ -377,14 +411,14 @@ static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, int* max_active
   return 0;
 }
 
-template <int CS, int BC>
+template <int CS, int NG, int G>
 static int dispatch_gru_cluster(const GruArgs& a, cudaStream_t st, int* probe) {
   const int U = ceil_div(a.N, CS);
   const int upw = ceil_div(U, GRU_WARPS);
   const int jc = ceil_div(CS * ((U + 3) & ~3), 128);     // padded h vector: CS slices of pitch round4(U)
   if (upw > 4 || jc > 4) return -1;
 #define SG_GRU_CASE(J, P) \
-  if (jc == J && upw == P) return launch_gru_cluster<J, P, CS, BC>(a, st, probe);
+  if (jc == J && upw == P) return launch_gru_cluster<J, P, CS, NG, G>(a, st, probe);
   SG_GRU_CASE(1, 1) SG_GRU_CASE(1, 2) SG_GRU_CASE(1, 3) SG_GRU_CASE(1, 4)
   SG_GRU_CASE(2, 1) SG_GRU_CASE(2, 2) SG_GRU_CASE(2, 3) SG_GRU_CASE(2, 4)
   SG_GRU_CASE(3, 1) SG_GRU_CASE(3, 2) SG_GRU_CASE(3, 3) SG_GRU_CASE(3, 4)
@@ -458,29 +492,43 @@ int gru_input_proj(const GruArgs& a, cudaStream_t st) {
 }
 
 // scratch: 2*B*N floats (ping-pong hidden state) for the generic path
-int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st) {
+int gru_keyquery_forward(const GruArgs& a_in, int path, float* scratch, cudaStream_t st) {
+  GruArgs a = a_in;
   SG_CHECK(a.B > 0 && a.N > 0 && a.W > 0, "gru: bad dims B=%d N=%d W=%d", a.B, a.N, a.W);
+  a.xrep = 1;
+  if (const char* e = getenv("STEMGNN_GRU_XREP")) a.xrep = atoi(e) > 0 ? atoi(e) : 1;
   SG_TRY(gru_input_proj(a, st));
   if (path != 1) {
-    // 16-CTA clusters, 4 sequences each; if the device cannot keep ceil(B/4) clusters resident at
-    // once (B200: 7 clusters of 16) but can with 5 sequences per cluster, use 5 and stay in one wave.
+    // 16-CTA clusters with one group of 4 (or 5, to stay within the 7 resident clusters of a B200)
+    // sequences each.  STEMGNN_GRU_MODE=ng*10+g forces a configuration, incl. the two-group pipelined
+    // variants 22 / 23 (tests, measurements).
+    int force = 0;
+    if (const char* e = getenv("STEMGNN_GRU_MODE")) force = atoi(e);
     int max_active = 0;
-    int rc = dispatch_gru_cluster<16, 4>(a, st, &max_active);
+    int rc = dispatch_gru_cluster<16, 1, 4>(a, st, &max_active);
     if (rc == 0) {
-      const int need4 = ceil_div(a.B, 4), need5 = ceil_div(a.B, 5);
-      if (need4 > max_active && need5 <= max_active && need4 <= 2 * max_active) {
-        rc = dispatch_gru_cluster<16, 5>(a, st, nullptr);
-        if (rc == 0) return 0;
-        if (rc > 0) return rc;
+      const int mx = max_active > 0 ? max_active : 1;
+      int mode = force;
+      if (mode == 0) {
+        // measured on B200 (profiles/README.md): one group of 5 sequences in a single wave beats both
+        // 4 sequences in two waves and two software-pipelined groups (the DSMEM stores of one group
+        // stall the LDS-heavy mat-vec of the other), so the pipelined modes are opt-in only.
+        if (ceil_div(a.B, 4) <= mx) mode = 14;
+        else if (ceil_div(a.B, 5) <= mx) mode = 15;
+        else mode = 14;
       }
-      rc = dispatch_gru_cluster<16, 4>(a, st, nullptr);
+      if (mode == 22) rc = dispatch_gru_cluster<16, 2, 2>(a, st, nullptr);
+      else if (mode == 23) rc = dispatch_gru_cluster<16, 2, 3>(a, st, nullptr);
+      else if (mode == 15) rc = dispatch_gru_cluster<16, 1, 5>(a, st, nullptr);
+      else rc = dispatch_gru_cluster<16, 1, 4>(a, st, nullptr);
+      if (rc < 0) rc = dispatch_gru_cluster<16, 1, 4>(a, st, nullptr);
       if (rc == 0) return 0;
       if (rc > 0) return rc;
     } else if (rc > 0) {
       return rc;
     }
     if (a.N <= 256) {
-      rc = dispatch_gru_cluster<8, 4>(a, st, nullptr);
+      rc = dispatch_gru_cluster<8, 1, 4>(a, st, nullptr);
       if (rc == 0) return 0;
       if (rc > 0) return rc;
     }

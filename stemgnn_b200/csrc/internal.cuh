@@ -19,6 +19,7 @@ struct GruArgs {
   float* gi;           // (N, B, 3N) scratch: input projection of every step
   float* g_r; float* g_z; float* g_n; float* g_hn;   // (N, B, N) gate values saved for BPTT (or null)
   int B, N, W;
+  int xrep;            // measurement knob: redundant DSMEM sends per step (1 = normal)
 };
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
 
