@@ -603,22 +603,27 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
   // ---- BPTT through the GRU (base_model.py:137) ----
   GruBwdArgs ga = {p->gru_w_hh, p->weight_key, p->weight_query, w.d_key, w.d_query, ws.h_all,
                    ws.g_r, ws.g_z, ws.g_n, ws.g_hn, w.dgh, ws.gi /* reused as dgi */, B, N};
-  SG_CUDA(cudaMemsetAsync(w.dh[0], 0, (size_t)R * sizeof(float), st));
-  const size_t smem = (size_t)(4 * 3 * N + 4 * N + 8 * 4 * 32) * sizeof(float);
-  SG_CHECK(smem <= 200 * 1024, "gru backward: N=%d too large for the step kernel", N);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    SG_CUDA(cudaFuncSetAttribute(gru_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  int brc = gru_bwd_cluster(p->gru_w_hh, p->weight_key, p->weight_query, w.d_key, w.d_query, ws.h_all, ws.g_r,
+                            ws.g_z, ws.g_n, ws.g_hn, w.dgh, ws.gi, B, N, st);
+  if (brc > 0) return brc;
+  if (brc < 0) {   // generic fallback: one launch per step, W_hh streamed from L2
+    SG_CUDA(cudaMemsetAsync(w.dh[0], 0, (size_t)R * sizeof(float), st));
+    const size_t smem = (size_t)(4 * 3 * N + 4 * N + 8 * 4 * 32) * sizeof(float);
+    SG_CHECK(smem <= 200 * 1024, "gru backward: N=%d too large for the step kernel", N);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      SG_CUDA(cudaFuncSetAttribute(gru_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    dim3 bgrid(ceil_div(N, 32), ceil_div(B, 4));
+    int cur = 0;
+    for (int s = N - 1; s >= 0; --s) {
+      gru_bwd_step_kernel<<<bgrid, 256, smem, st>>>(ga, s, w.dh[cur], w.dh[cur ^ 1]);
+      count_launch();
+      cur ^= 1;
+    }
+    SG_LAUNCH_CHECK("gru_bwd_step_kernel");
   }
-  dim3 bgrid(ceil_div(N, 32), ceil_div(B, 4));
-  int cur = 0;
-  for (int s = N - 1; s >= 0; --s) {
-    gru_bwd_step_kernel<<<bgrid, 256, smem, st>>>(ga, s, w.dh[cur], w.dh[cur ^ 1]);
-    count_launch();
-    cur ^= 1;
-  }
-  SG_LAUNCH_CHECK("gru_bwd_step_kernel");
   const float* dgh = w.dgh;
   const float* dgi = ws.gi;
   const int SB = N * B;

@@ -427,6 +427,267 @@ static int dispatch_gru_cluster(const GruArgs& a, cudaStream_t st, int* probe) {
   return -1;
 }
 
+// =================================================================================================
+// BPTT through the recurrence on the same cluster layout (backward of base_model.py:137).
+//
+// Per step s = N-1 .. 0 every CTA (i) sums the 16 partial d h_s slices it received, adds the direct
+// key/query terms, and turns them into the gate gradients of ITS hidden units (written to DGH / DGI
+// for the weight-gradient GEMMs); (ii) multiplies them with its resident rows of W_hh:
+// partial[b][k] = sum_{own rows} d_gh[b][row] W_hh[row][k] for ALL k (lanes own distinct k, so there is
+// no cross-lane reduction; the 8 warps' row groups are combined through shared memory); (iii) sends the
+// slice of `partial` that belongs to CTA p's units to CTA p (reduce-scatter over DSMEM with st.async +
+// mbarrier, same transport as the forward).  W_hh never leaves shared memory: one launch instead of N.
+struct GruBwdClusterArgs {
+  const float* w_hh; const float* wk; const float* wq;
+  const float* d_key; const float* d_query;
+  const float* h_all; const float* g_r; const float* g_z; const float* g_n; const float* g_hn;
+  float* dgh; float* dgi;            // (S*B, 3N)
+  int B, N;
+};
+
+template <int JC, int UPW, int CS, int G>
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_cluster_kernel(GruBwdClusterArgs a) {
+  constexpr int KP = 128 * JC;
+  constexpr int KQ = KP / 4;                // float4 chunks per padded h vector
+  constexpr int ULOC = GRU_WARPS * UPW;
+  constexpr int ROWS = 3 * UPW;
+  static_assert(UPW * G <= 32, "finalising lanes");
+
+  extern __shared__ __align__(16) float smem[];
+  float* Wsm = smem;                                  // [3*ULOC][KP]
+  float* red = Wsm + 3 * ULOC * KP;                   // [WARPS][G][KP] per-warp partial products
+  float* recv = red + GRU_WARPS * G * KP;             // [2][CS][G][32] received d h slices
+  float2* coef = reinterpret_cast<float2*>(recv + 2 * CS * G * 32);   // [3*ULOC][G] {g,g}
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(coef + 3 * ULOC * G);  // [2]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int N = a.N, B = a.B;
+  const int U = (N + CS - 1) / CS;
+  const int UP = (U + 3) & ~3;
+  const int UP4 = UP >> 2;
+  const int u0 = q * U;
+  const int b0 = cid * G;
+
+  for (int idx = tid; idx < 3 * ULOC * KP; idx += GRU_THREADS) {
+    const int row = idx / KP, kp = idx - row * KP;
+    const int lu = row / 3, gate = row - lu * 3;
+    const int u = u0 + lu;
+    const int src_cta = kp / UP, src_lu = kp - src_cta * UP;
+    const int k = src_cta * U + src_lu;
+    float v = 0.f;
+    if (lu < U && u < N && src_cta < CS && src_lu < U && k < N)
+      v = __ldg(a.w_hh + ((long long)gate * N + u) * N + k);
+    Wsm[idx] = v;
+  }
+  for (int idx = tid; idx < 2 * CS * G * 32; idx += GRU_THREADS) recv[idx] = 0.f;
+  for (int idx = tid; idx < 3 * ULOC * G; idx += GRU_THREADS) coef[idx] = make_float2(0.f, 0.f);
+  if (tid == 0) {
+    mbar_init_(&rbar[0], 1);
+    mbar_init_(&rbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t tx_bytes = (uint32_t)(CS * G * UP * sizeof(float));
+
+  // reduce-scatter descriptors: this thread combines float4 chunk (b, kq) of the 8 warp partials and
+  // sends it to the CTA that owns hidden positions [4kq, 4kq+4)
+  constexpr int ITEMS = (G * KQ + GRU_THREADS - 1) / GRU_THREADS;
+  int it_off[ITEMS];
+  uint32_t it_dst[ITEMS], it_bar[ITEMS];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int c = tid + it * GRU_THREADS;
+    it_off[it] = -1;
+    it_dst[it] = it_bar[it] = 0;
+    if (c < G * KQ) {
+      const int bb = c / KQ, kq = c - bb * KQ;
+      const int dest = kq / UP4, i4 = kq - dest * UP4;
+      if (dest < CS) {
+        it_off[it] = bb * KP + 4 * kq;
+        it_dst[it] = map_to_cta(smem_addr_u32(recv + (q * G + bb) * 32 + 4 * i4), (uint32_t)dest);
+        it_bar[it] = map_to_cta(smem_addr_u32(&rbar[0]), (uint32_t)dest);
+      }
+    }
+  }
+
+  // finalising lanes: lane t < UPW*G owns (local unit w*UPW + t/G, sequence t%G)
+  const int fi = lane / G, fb = lane - fi * G;
+  const int lu = w * UPW + fi;
+  const int u = u0 + lu;
+  const bool flane = lane < UPW * G;
+  const bool bvalid = (b0 + fb) < B;
+  const bool fin = flane && (lu < U) && (u < N) && bvalid;
+  float dk = 0.f, dq = 0.f;
+  if (fin) {
+    dk = __ldg(a.d_key + (long long)(b0 + fb) * N + u);
+    dq = __ldg(a.d_query + (long long)(b0 + fb) * N + u);
+  }
+  // saved gates of step s for this lane, requested one step ahead
+  auto load_gates = [&](int s, float& r, float& z, float& n, float& hn, float& hp) {
+    r = z = n = hn = hp = 0.f;
+    if (fin) {
+      const long long e = ((long long)s * B + (b0 + fb)) * N + u;
+      r = __ldg(a.g_r + e); z = __ldg(a.g_z + e); n = __ldg(a.g_n + e); hn = __ldg(a.g_hn + e);
+      if (s > 0) hp = __ldg(a.h_all + e - (long long)B * N);
+    }
+  };
+  float gr, gz, gn, ghn, ghp;
+  load_gates(N - 1, gr, gz, gn, ghn, ghp);
+  float carry = 0.f;       // dh_s * z_s : direct path into dh_{s-1} of the same (unit, sequence)
+
+  __syncthreads();
+  cluster.sync();
+
+  for (int s = N - 1; s >= 0; --s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    if (tid == 0 && s > 0) mbar_expect_tx_(&rbar[nxt], tx_bytes);
+    if (s < N - 1) mbar_wait_cluster_(&rbar[cur], (uint32_t)((N - 2 - s) >> 1) & 1u);
+    float nr = 0.f, nz = 0.f, nn = 0.f, nhn = 0.f, nhp = 0.f;
+    if (s > 0) load_gates(s - 1, nr, nz, nn, nhn, nhp);
+    // (i) gate gradients of the own units
+    if (flane) {
+      float d_r = 0.f, d_z = 0.f, d_np = 0.f, d_hn = 0.f;
+      if (fin) {
+        float dh = carry + dk * __ldg(a.wk + s) + dq * __ldg(a.wq + s);
+        if (s < N - 1) {
+          const float* rp = recv + (cur * CS * G + fb) * 32 + lu;
+#pragma unroll
+          for (int src = 0; src < CS; ++src) dh += rp[src * G * 32];
+        }
+        const float dn = dh * (1.f - gz);
+        d_np = dn * (1.f - gn * gn);
+        d_z = dh * (ghp - gn) * gz * (1.f - gz);
+        d_r = d_np * ghn * gr * (1.f - gr);
+        d_hn = d_np * gr;
+        carry = dh * gz;
+        const long long o = ((long long)s * B + (b0 + fb)) * 3 * N + u;
+        a.dgh[o] = d_r; a.dgh[o + N] = d_z; a.dgh[o + 2 * N] = d_hn;
+        a.dgi[o] = d_r; a.dgi[o + N] = d_z; a.dgi[o + 2 * N] = d_np;
+      }
+      coef[(lu * 3 + 0) * G + fb] = make_float2(d_r, d_r);
+      coef[(lu * 3 + 1) * G + fb] = make_float2(d_z, d_z);
+      coef[(lu * 3 + 2) * G + fb] = make_float2(d_hn, d_hn);
+    }
+    gr = nr; gz = nz; gn = nn; ghn = nhn; ghp = nhp;
+    if (s == 0) break;                      // dh_{-1} is not needed
+    __syncthreads();
+    // (ii) partial[b][k] over this warp's rows; lane owns k' = 128 j + 4 lane + {0..3}
+    float2 acc[G][JC][2];
+#pragma unroll
+    for (int bb = 0; bb < G; ++bb)
+#pragma unroll
+      for (int j = 0; j < JC; ++j) acc[bb][j][0] = acc[bb][j][1] = make_float2(0.f, 0.f);
+    const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * lane;
+    const float2* cbase = coef + (w * ROWS) * G;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float4 wv[JC];
+#pragma unroll
+      for (int j = 0; j < JC; ++j) wv[j] = *reinterpret_cast<const float4*>(wbase + r * KP + 128 * j);
+#pragma unroll
+      for (int bb = 0; bb < G; ++bb) {
+        const float2 g2 = cbase[r * G + bb];
+#pragma unroll
+        for (int j = 0; j < JC; ++j) {
+          acc[bb][j][0] = __ffma2_rn(make_float2(wv[j].x, wv[j].y), g2, acc[bb][j][0]);
+          acc[bb][j][1] = __ffma2_rn(make_float2(wv[j].z, wv[j].w), g2, acc[bb][j][1]);
+        }
+      }
+    }
+    float* myred = red + (long long)w * G * KP + 4 * lane;
+#pragma unroll
+    for (int bb = 0; bb < G; ++bb)
+#pragma unroll
+      for (int j = 0; j < JC; ++j)
+        *reinterpret_cast<float4*>(myred + bb * KP + 128 * j) =
+            make_float4(acc[bb][j][0].x, acc[bb][j][0].y, acc[bb][j][1].x, acc[bb][j][1].y);
+    __syncthreads();
+    // (iii) combine the 8 row groups and reduce-scatter to the owners of each hidden slice
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      if (it_off[it] >= 0) {
+        float4 v = *reinterpret_cast<const float4*>(red + it_off[it]);
+#pragma unroll
+        for (int ww = 1; ww < GRU_WARPS; ++ww) {
+          const float4 t = *reinterpret_cast<const float4*>(red + (long long)ww * G * KP + it_off[it]);
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        st_async_v4(it_dst[it] + (uint32_t)nxt * (CS * G * 32 * 4), v, it_bar[it] + (uint32_t)nxt * 8);
+      }
+    }
+  }
+  cluster.sync();
+}
+
+template <int JC, int UPW, int CS, int G>
+static int launch_gru_bwd_cluster(const GruBwdClusterArgs& a, cudaStream_t st) {
+  constexpr int KP = 128 * JC;
+  constexpr int ULOC = GRU_WARPS * UPW;
+  const size_t smem = (size_t)(3 * ULOC * KP + GRU_WARPS * G * KP + 2 * CS * G * 32 + 2 * 3 * ULOC * G) * sizeof(float) +
+                      2 * sizeof(uint64_t);
+  if (smem > 227 * 1024) return -1;
+  auto kern = gru_bwd_cluster_kernel<JC, UPW, CS, G>;
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  const int nclusters = ceil_div(a.B, G);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CS);
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!attr_set) {
+    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      max_clusters = 0;
+    }
+    attr_set = true;
+  }
+  if (max_clusters < 1) return -1;
+  SG_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  count_launch();
+  return 0;
+}
+
+// returns 0 launched, -1 unsupported here (caller falls back to the per-step kernels), >0 error
+int gru_bwd_cluster(const float* w_hh, const float* wk, const float* wq, const float* d_key,
+                    const float* d_query, const float* h_all, const float* g_r, const float* g_z,
+                    const float* g_n, const float* g_hn, float* dgh, float* dgi, int B, int N,
+                    cudaStream_t st) {
+  if (getenv("STEMGNN_BPTT_STEPWISE") != nullptr) return -1;
+  constexpr int CS = 16;
+  GruBwdClusterArgs a = {w_hh, wk, wq, d_key, d_query, h_all, g_r, g_z, g_n, g_hn, dgh, dgi, B, N};
+  const int U = ceil_div(N, CS);
+  const int upw = ceil_div(U, GRU_WARPS);
+  const int jc = ceil_div(CS * ((U + 3) & ~3), 128);
+  if (upw > 4 || jc > 4) return -1;
+  const bool g5 = ceil_div(B, 4) > 7 && ceil_div(B, 5) <= 7;     // same wave rule as the forward
+#define SG_BWD_CASE(J, P)                                                        \
+  if (jc == J && upw == P) {                                                     \
+    if (g5) {                                                                    \
+      const int rc = launch_gru_bwd_cluster<J, P, CS, 5>(a, st);                 \
+      if (rc >= 0) return rc;                                                    \
+    }                                                                            \
+    return launch_gru_bwd_cluster<J, P, CS, 4>(a, st);                           \
+  }
+  SG_BWD_CASE(1, 1) SG_BWD_CASE(1, 2) SG_BWD_CASE(2, 1) SG_BWD_CASE(2, 2) SG_BWD_CASE(2, 3)
+  SG_BWD_CASE(3, 2) SG_BWD_CASE(3, 3) SG_BWD_CASE(3, 4) SG_BWD_CASE(4, 3) SG_BWD_CASE(4, 4)
+  SG_BWD_CASE(1, 3) SG_BWD_CASE(1, 4) SG_BWD_CASE(2, 4) SG_BWD_CASE(3, 1) SG_BWD_CASE(4, 1) SG_BWD_CASE(4, 2)
+#undef SG_BWD_CASE
+  return -1;
+}
+
 // ---- generic path: one launch per step, W_hh streamed from L2 --------------------------------
 // grid.x = ceil(N / 4) (one warp per hidden unit), loops over the batch in chunks of 4.
 __global__ void __launch_bounds__(128) gru_step_kernel(GruArgs a, int s, const float* __restrict__ h_prev,

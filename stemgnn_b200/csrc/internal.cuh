@@ -22,6 +22,11 @@ struct GruArgs {
   int xrep;            // measurement knob: redundant DSMEM sends per step (1 = normal)
 };
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
+// persistent-cluster BPTT (one launch); -1 = unsupported here, use the per-step kernels
+int gru_bwd_cluster(const float* w_hh, const float* wk, const float* wq, const float* d_key,
+                    const float* d_query, const float* h_all, const float* g_r, const float* g_z,
+                    const float* g_n, const float* g_hn, float* dgh, float* dgi, int B, int N,
+                    cudaStream_t st);
 
 // ---- attention / Laplacian (latent.cu) ----------------------------------------------------------------
 struct AttnArgs {
