@@ -56,7 +56,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
     b.w1f = take(4 * d * 4 * W);
     b.ic = take(2 * T * T);
     b.ri = take(8 * T * T);
-    b.wout = take(8 * T * (T + W));
+    b.wout = take(8 * T * ((T + W + 15) / 16 * 16));   // woutT: (round16(T+W), 8T), pad rows zero
     b.act1 = take(2 * R * d);
     b.act2 = take(2 * R * d);
     b.act3 = take(R * 2 * d);
@@ -77,6 +77,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
     w.d_fsum = take(R * W);
     w.d_pre = take(R * (T + W)); w.negdz = take(R * W); w.d_act3 = take(R * 2 * d);
     w.d_wout = take(8 * T * (T + W)); w.d_ri = take(8 * T * T); w.d_w1f = take(4 * d * 3 * W);
+    w.dlrT = take(2 * d * ((R + 3) / 4 * 4)); w.inT = take(d * ((R + 3) / 4 * 4)); w.wsT = take(d * 2 * d);
     w.dlr = take(R * 2 * d); w.d_act[0] = take(R * d); w.d_act[1] = take(R * d);
     w.d_G = take(R * 3 * W); w.d_Gp = take(R * 3 * W);
     w.d_bc = take(R * W); w.d_x0 = take(R * W); w.d_mul_L = take(4 * N * N);
@@ -135,13 +136,16 @@ int fold_block_weights(const stemgnn_dims_t& dm, const stemgnn_block_params_t& b
     EpiAxpby epi = {b.ri + (size_t)c * 4 * T * T, T, (long long)T * T, nullptr, 0, 0, 1.f, 0.f};
     SG_TRY((launch_sgemm<false, false, false>(g, epi, 4, st, "fold_out_ri")));
   }
-  {   // wout[:, 0:T] = RI @ forecast.weight^T ; wout[:, T:T+W] = RI @ backcast.weight^T
-    GemmOperands g = {b.ri, T, 0, bp.forecast_w, T, 0, nullptr, 8 * T, T, T};
-    EpiAxpby epi = {b.wout, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+  {   // woutT[o][c] = sum_u W{f,b}[o][u] RI[c][u]  (rows 0..T-1: forecast.weight, T..T+W-1: backcast.weight)
+    const int PWp = (PW + 15) / 16 * 16;
+    if (PWp > PW)
+      SG_CUDA(cudaMemsetAsync(b.wout + (size_t)PW * 8 * T, 0, (size_t)(PWp - PW) * 8 * T * sizeof(float), st));
+    GemmOperands g = {bp.forecast_w, T, 0, b.ri, T, 0, nullptr, T, 8 * T, T};
+    EpiAxpby epi = {b.wout, 8 * T, 0, nullptr, 0, 0, 1.f, 0.f};
     SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "fold_out_forecast")));
     if (stack_idx == 0) {
-      GemmOperands g2 = {b.ri, T, 0, bp.backcast_w, T, 0, nullptr, 8 * T, W, T};
-      EpiAxpby epi2 = {b.wout + T, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+      GemmOperands g2 = {bp.backcast_w, T, 0, b.ri, T, 0, nullptr, W, 8 * T, T};
+      EpiAxpby epi2 = {b.wout + (size_t)T * 8 * T, 8 * T, 0, nullptr, 0, 0, 1.f, 0.f};
       SG_TRY((launch_sgemm<false, true, false>(g2, epi2, 1, st, "fold_out_backcast")));
     }
   }
@@ -177,10 +181,18 @@ int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, in
   if (!reuse_folded) SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
   SG_TRY(launch_gft(mul_L, x_bwn, b.G, B, N, W, st));
   SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st));
-  {
-    GemmOperands g = {b.act3, 2 * d, 0, b.wout, PW, 0, nullptr, R, PW, 2 * d};
-    EpiAxpby epi = {b.pre, PW, 0, nullptr, 0, 0, 1.f, 0.f};
-    SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "out_gemm")));
+  {   // pre = [real3 | imag3] @ woutT^T : tcgen05 TF32 unless exact fp32 is requested
+    int rc = -1;
+    if (gemm_mode != 1)
+      rc = tc_gemm(R, (PW + 15) / 16 * 16, 2 * d, 1.f, b.act3, 2 * d, b.wout, 2 * d, (PW + 15) / 16 * 16, b.pre,
+                   nullptr, 0, PW, PW, 0, 1, st);
+    if (rc > 0) return rc;
+    if (rc < 0) {
+      SG_CHECK(gemm_mode != 2 || true, "unreachable");
+      GemmOperands g = {b.act3, 2 * d, 0, b.wout, 2 * d, 0, nullptr, R, PW, 2 * d};
+      EpiAxpby epi = {b.pre, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+      SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "out_gemm")));
+    }
   }
   HeadArgs h = {};
   h.pre = b.pre; h.ldp = PW; h.x_bnw = x_bnw;

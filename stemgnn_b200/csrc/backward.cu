@@ -144,6 +144,80 @@ __global__ void __launch_bounds__(256) glu_gate_bwd_kernel(const float* __restri
   }
 }
 
+// out[c*ldo + r] = in[r*ldi + c]   (32x32 shared-memory tiles)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int rows, int cols, int ldi,
+                                                        float* __restrict__ out, int ldo) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 32; rr += 8)
+    tile[rr][tx] = (r0 + rr < rows && c0 + tx < cols) ? in[(long long)(r0 + rr) * ldi + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8)
+    if (c0 + cc < cols && r0 + tx < rows) out[(long long)(c0 + cc) * ldo + r0 + tx] = tile[tx][cc];
+}
+static int transpose(cudaStream_t st, const float* in, int rows, int cols, int ldi, float* out, int ldo) {
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  transpose_kernel<<<grid, 256, 0, st>>>(in, rows, cols, ldi, out, ldo);
+  SG_LAUNCH_CHECK("transpose_kernel");
+  return 0;
+}
+
+// GLU gate backward fused with (i) the bias gradients (column sums of dl / dr) and (ii) the transposed
+// copy dlrT (2N, ldT) that the tensor-core weight-gradient GEMM consumes as its K-major A operand.
+__global__ void __launch_bounds__(256) glu_gate_bwd_fused_kernel(
+    const float* __restrict__ d_out, int ldd, const float* __restrict__ l, const float* __restrict__ s, int R,
+    int N, float* __restrict__ dlr, float* __restrict__ dlrT, int ldT, float* __restrict__ dbl,
+    float* __restrict__ dbr) {
+  __shared__ float tl[32][33], tr[32][33];
+  __shared__ float cs[2][8][32];
+  const int n0 = blockIdx.x * 32;
+  const int rbase = blockIdx.y * 256;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = n0 + tx;
+  float sl = 0.f, sr = 0.f;
+  for (int sub = 0; sub < 8; ++sub) {
+    const int r0 = rbase + sub * 32;
+    if (r0 >= R) break;
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int row = r0 + rr;
+      float dl = 0.f, dr = 0.f;
+      if (row < R && n < N) {
+        const float dv = d_out[(long long)row * ldd + n];
+        const float sv = s[(long long)row * N + n], lv = l[(long long)row * N + n];
+        dl = dv * sv;
+        dr = dv * lv * sv * (1.f - sv);
+        dlr[(long long)row * 2 * N + n] = dl;
+        dlr[(long long)row * 2 * N + N + n] = dr;
+      }
+      tl[rr][tx] = dl;
+      tr[rr][tx] = dr;
+      sl += dl;
+      sr += dr;
+    }
+    __syncthreads();
+    if (dlrT != nullptr) {
+      for (int cc = ty; cc < 32; cc += 8) {
+        if (n0 + cc < N && r0 + tx < R) {
+          dlrT[(long long)(n0 + cc) * ldT + r0 + tx] = tl[tx][cc];
+          dlrT[(long long)(N + n0 + cc) * ldT + r0 + tx] = tr[tx][cc];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cs[0][ty][tx] = sl;
+  cs[1][ty][tx] = sr;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += cs[0][i][tx]; c += cs[1][i][tx]; }
+    if (dbl != nullptr) atomicAdd(dbl + n, a);
+    if (dbr != nullptr) atomicAdd(dbr + n, c);
+  }
+}
+
 // ---- unfold the gradient of DFT-folded first-layer weights (transpose of fold_in_kernel) -----------------------
 // d_w[o][(kp+1)*W + f] += sum_t d_wf[o][kp*W + t] * tw(chain, f, t)
 __global__ void fold_in_bwd_kernel(const float* __restrict__ d_wf, float* __restrict__ d_w, int d, int W,
@@ -434,7 +508,7 @@ static int block_backward(const stemgnn_dims_t& dm, const stemgnn_block_params_t
                           const stemgnn_block_grads_t& gr, int stack_idx, const float* x_bnw,
                           const float* x_bwn, const float* mul_L, const BlockWs& b, const BwdWs& w,
                           const float* d_forecast, const float* d_bc, float* d_xin, float* d_mul_L,
-                          int first_mulL_writer, cudaStream_t st) {
+                          int first_mulL_writer, int gemm_mode, cudaStream_t st) {
   const int B = dm.B, N = dm.N, W = dm.W, T = dm.multi * W, d = 4 * T, R = B * N;
   const int PW = (stack_idx == 0) ? T + W : T;
   // (1) head
@@ -454,16 +528,17 @@ static int block_backward(const stemgnn_dims_t& dm, const stemgnn_block_params_t
       xin_written = true;
     }
   }
-  // (2) folded output map: pre = act3 @ wout
-  SG_TRY((gemm<false, true>(st, R, 2 * d, PW, 1.f, w.d_pre, PW, b.wout, PW, 0.f, w.d_act3, 2 * d, "d_act3")));
+  // (2) folded output map: pre = act3 @ woutT^T,  woutT (PW, 8T) = [Wf; Wb] @ RI^T
+  SG_TRY((gemm<false, false>(st, R, 2 * d, PW, 1.f, w.d_pre, PW, b.wout, 2 * d, 0.f, w.d_act3, 2 * d, "d_act3")));
   SG_CUDA(cudaMemsetAsync(w.d_wout, 0, (size_t)8 * T * PW * sizeof(float), st));
-  SG_TRY((gemm_acc<true, false>(st, 2 * d, PW, R, b.act3, 2 * d, w.d_pre, PW, w.d_wout, PW, "d_wout")));
-  //   wout[:, :T] = RI @ Wf^T ; wout[:, T:] = RI @ Wb^T
-  SG_TRY((gemm_acc<true, false>(st, T, T, 8 * T, w.d_wout, PW, b.ri, T, gr.forecast_w, T, "d_forecast_w")));
-  SG_TRY((gemm<false, false>(st, 8 * T, T, T, 1.f, w.d_wout, PW, bp.forecast_w, T, 0.f, w.d_ri, T, "d_ri_f")));
+  SG_TRY((gemm_acc<true, false>(st, PW, 2 * d, R, w.d_pre, PW, b.act3, 2 * d, w.d_wout, 2 * d, "d_woutT")));
+  SG_TRY((gemm_acc<false, false>(st, T, T, 8 * T, w.d_wout, 8 * T, b.ri, T, gr.forecast_w, T, "d_forecast_w")));
+  SG_TRY((gemm<true, false>(st, 8 * T, T, T, 1.f, w.d_wout, 8 * T, bp.forecast_w, T, 0.f, w.d_ri, T, "d_ri_f")));
   if (stack_idx == 0) {
-    SG_TRY((gemm_acc<true, false>(st, W, T, 8 * T, w.d_wout + T, PW, b.ri, T, gr.backcast_w, T, "d_backcast_w")));
-    SG_TRY((gemm<false, false>(st, 8 * T, T, W, 1.f, w.d_wout + T, PW, bp.backcast_w, T, 1.f, w.d_ri, T, "d_ri_b")));
+    SG_TRY((gemm_acc<false, false>(st, W, T, 8 * T, w.d_wout + (size_t)T * 8 * T, 8 * T, b.ri, T, gr.backcast_w, T,
+                                  "d_backcast_w")));
+    SG_TRY((gemm<true, false>(st, 8 * T, T, W, 1.f, w.d_wout + (size_t)T * 8 * T, 8 * T, bp.backcast_w, T, 1.f,
+                              w.d_ri, T, "d_ri_b")));
   }
   //   RI[c][k*T+f][u] = sum_t ic[c][f][t] weight[k][t][u]  ->  d_weight[k][t][u] += sum_{c,f} ic[c][f][t] d_RI
   if (gr.weight != nullptr) {
@@ -482,18 +557,41 @@ static int block_backward(const stemgnn_dims_t& dm, const stemgnn_block_params_t
     int ldd = 2 * d;
     for (int layer = 2; layer >= 0; --layer) {
       const int gidx = 2 * layer + c;
-      glu_gate_bwd_kernel<<<nblocks((long long)R * d, 256, 32768), 256, 0, st>>>(d_out, ldd, b.save_l[gidx],
-                                                                                b.save_s[gidx], R, d, w.dlr);
-      SG_LAUNCH_CHECK("glu_gate_bwd_kernel");
-      SG_TRY(colsum_acc(st, w.dlr, R, d, 2 * d, 1.f, gr.glu_left_b[gidx]));
-      SG_TRY(colsum_acc(st, w.dlr + d, R, d, 2 * d, 1.f, gr.glu_right_b[gidx]));
+      const int ldT = (R + 3) / 4 * 4;
+      const bool tc = (gemm_mode != 1) && layer > 0 && gr.glu_left_w[gidx] != nullptr &&
+                      gr.glu_right_w[gidx] != nullptr;
+      {
+        dim3 ggrid(ceil_div(d, 32), ceil_div(R, 256));
+        glu_gate_bwd_fused_kernel<<<ggrid, 256, 0, st>>>(d_out, ldd, b.save_l[gidx], b.save_s[gidx], R, d, w.dlr,
+                                                        tc ? w.dlrT : nullptr, ldT, gr.glu_left_b[gidx],
+                                                        gr.glu_right_b[gidx]);
+        SG_LAUNCH_CHECK("glu_gate_bwd_fused_kernel");
+      }
       if (layer > 0) {
         const float* in = (layer == 2 ? b.act2 : b.act1) + (size_t)c * R * d;
-        SG_TRY((gemm_acc<true, false>(st, d, d, R, w.dlr, 2 * d, in, d, gr.glu_left_w[gidx], d, "d_glu_left_w")));
-        SG_TRY((gemm_acc<true, false>(st, d, d, R, w.dlr + d, 2 * d, in, d, gr.glu_right_w[gidx], d, "d_glu_right_w")));
         float* d_in = w.d_act[layer & 1];
-        SG_TRY((gemm<false, false>(st, R, d, d, 1.f, w.dlr, 2 * d, bp.glu_left_w[gidx], d, 0.f, d_in, d, "d_act_l")));
-        SG_TRY((gemm<false, false>(st, R, d, d, 1.f, w.dlr + d, 2 * d, bp.glu_right_w[gidx], d, 1.f, d_in, d, "d_act_r")));
+        int rc = -1;
+        if (tc) {
+          // weight gradients: [dWl; dWr] (2d x d) += dlrT (2d x R) . inT (d x R)^T   (K = R, split-K atomics)
+          SG_TRY(transpose(st, in, R, d, d, w.inT, ldT));
+          rc = tc_gemm(2 * d, d, R, 1.f, w.dlrT, ldT, w.inT, ldT, d, gr.glu_left_w[gidx], gr.glu_right_w[gidx], d, d,
+                       d, 1, 12, st);
+          if (rc > 0) return rc;
+          if (rc == 0) {
+            // input gradient: d_in (R x d) = dlr (R x 2d) . [Wl^T | Wr^T] (d x 2d)^T
+            SG_TRY(transpose(st, bp.glu_left_w[gidx], d, d, d, w.wsT, 2 * d));
+            SG_TRY(transpose(st, bp.glu_right_w[gidx], d, d, d, w.wsT + d, 2 * d));
+            rc = tc_gemm(R, d, 2 * d, 1.f, w.dlr, 2 * d, w.wsT, 2 * d, d, d_in, nullptr, 0, d, d, 0, 1, st);
+            if (rc > 0) return rc;
+            SG_CHECK(rc == 0, "tcgen05 backward GEMM rejected after the weight-gradient GEMM ran");
+          }
+        }
+        if (rc < 0) {
+          SG_TRY((gemm_acc<true, false>(st, d, d, R, w.dlr, 2 * d, in, d, gr.glu_left_w[gidx], d, "d_glu_left_w")));
+          SG_TRY((gemm_acc<true, false>(st, d, d, R, w.dlr + d, 2 * d, in, d, gr.glu_right_w[gidx], d, "d_glu_right_w")));
+          SG_TRY((gemm<false, false>(st, R, d, d, 1.f, w.dlr, 2 * d, bp.glu_left_w[gidx], d, 0.f, d_in, d, "d_act_l")));
+          SG_TRY((gemm<false, false>(st, R, d, d, 1.f, w.dlr + d, 2 * d, bp.glu_right_w[gidx], d, 1.f, d_in, d, "d_act_r")));
+        }
         d_out = d_in;
         ldd = d;
       } else {
@@ -558,9 +656,9 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
 
   // ---- blocks (reverse) ----
   SG_TRY(block_backward(dm, p->block[1], gr.block[1], 1, ws.blk[0].bc_bnw, ws.blk[0].bc_bwn, ws.mul_L,
-                        ws.blk[1], w, w.d_fsum, nullptr, w.d_bc, w.d_mul_L, 1, st));
+                        ws.blk[1], w, w.d_fsum, nullptr, w.d_bc, w.d_mul_L, 1, opts->gemm_mode, st));
   SG_TRY(block_backward(dm, p->block[0], gr.block[0], 0, ws.x_bnw, x, ws.mul_L, ws.blk[0], w, w.d_fsum,
-                        w.d_bc, d_x != nullptr ? w.d_x0 : nullptr, w.d_mul_L, 0, st));
+                        w.d_bc, d_x != nullptr ? w.d_x0 : nullptr, w.d_mul_L, 0, opts->gemm_mode, st));
 
   // ---- Chebyshev stack: L2 = 2 L L, L3 = 2 L L2 - L  (base_model.py:130-132) ----
   const float* L = ws.mul_L + nn;

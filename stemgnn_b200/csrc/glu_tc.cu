@@ -227,6 +227,124 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   }
 }
 
+// ---- generic TF32 GEMM: C[M,N] (+)= A[M,K] B[N,K]^T, both operands K-major ------------------------------
+// Same pipeline as glu_tc_kernel with one B operand.  gridDim.y splits K (partial sums are added with
+// atomics: gradient buffers accumulate by contract).  Rows m >= msplit go to the second output C1
+// (left / right weight gradients of a GLU layer come out of one GEMM).
+struct TcGemmArgs {
+  float* C0; float* C1; int ldc; int msplit;
+  int M, N, K;
+  int n_store;        // only columns < n_store are written (B rows beyond it are TMA zero fill)
+  int atomic;         // 1: C += acc (atomicAdd), 0: C = acc
+  float alpha;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int N = g.N;
+  const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)N * 128;
+  const uint32_t stage_bytes = a_bytes + w_bytes;
+  constexpr int STAGES = 3;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int total_kb = (g.K + TC_BK - 1) / TC_BK;
+  const int per = (total_kb + gridDim.y - 1) / gridDim.y;
+  const int kb0 = blockIdx.y * per;
+  const int kb1 = min(total_kb, kb0 + per);
+  const int num_kb = kb1 - kb0;     // may be <= 0 for trailing splits: nothing to add
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_2d(st, &map_a, &full_bar[s], (kb0 + i) * TC_BK, m0);
+          tma_load_2d(st + a_bytes, &map_b, &full_bar[s], (kb0 + i) * TC_BK, 0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_tf32(N);
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 8; ++kk)
+            umma_tf32(tmem_base, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int quarter = warp & 3;
+      const int row = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float* crow = nullptr;
+      if (row < g.M)
+        crow = row < g.msplit ? g.C0 + (size_t)row * g.ldc : g.C1 + (size_t)(row - g.msplit) * g.ldc;
+      for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (crow != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c + j < g.n_store) {
+              if (g.atomic) atomicAdd(crow + c + j, g.alpha * v[j]);
+              else crow[c + j] = g.alpha * v[j];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -289,6 +407,32 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   GluTcArgs g = {bl, br, out, ldo, save_l, save_s, lds, M, N, K};
   glu_tc_kernel<<<ceil_div(M, TC_BM), TC_THREADS, smem, st>>>(ma, ml, mr, g);
   SG_LAUNCH_CHECK("glu_tc_kernel");
+  return 0;
+}
+
+
+// C (+)= alpha * A[M,K] B[N,K]^T on tcgen05 TF32.  B may have fewer than N rows (n_rows_b): the missing
+// rows are TMA zero fill and n_store limits the written columns.  Returns -1 when the shape is unsupported.
+int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
+            float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st) {
+  if (N % 16 != 0 || N < 16 || N > 256 || K < 1 || (lda & 3) != 0 || (ldb & 3) != 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -1;
+  CUtensorMap ma, mb;
+  if (!make_map(enc, &ma, A, M, K, lda, TC_BM) || !make_map(enc, &mb, B, n_rows_b, K, ldb, N)) return -1;
+  const size_t smem = (size_t)3 * (TC_BM * 128 + (size_t)N * 128) + 64 + 1024;
+  if (smem > 227 * 1024) return -1;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    SG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  if (splits < 1) splits = 1;
+  TcGemmArgs g = {C0, C1 != nullptr ? C1 : C0, ldc, C1 != nullptr ? msplit : M, M, N, K, n_store, atomic, alpha};
+  dim3 grid(ceil_div(M, TC_BM), splits);
+  tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, g);
+  SG_LAUNCH_CHECK("tc_gemm_kernel");
   return 0;
 }
 

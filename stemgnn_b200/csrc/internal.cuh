@@ -77,13 +77,17 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
                 const float* Wr, const float* br, float* out, int ldo, float* save_l, float* save_s,
                 int lds, cudaStream_t st);
 
+// generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1
+int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
+            float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st);
+
 // ---- workspace ---------------------------------------------------------------------------------------
 struct BlockWs {
   float* G;        // (R, 3W | 4W) graph-Fourier rows
   float* w1f;      // [chain][side](d, ncol) DFT-folded first-layer weights
   float* ic;       // [2](T,T) inverse real DFT table
   float* ri;       // [2](4T, T) irfft o weight[k]
-  float* wout;     // (8T, T+W) folded output map
+  float* wout;     // woutT (round16(T+W), 8T): folded output map, K-major for the tensor-core GEMM
   float* act1;     // [chain](R, d)
   float* act2;     // [chain](R, d)
   float* act3;     // (R, 2d) = [real3 | imag3]
@@ -98,6 +102,7 @@ struct BlockWs {
 struct BwdWs {
   float *h_fsum, *h_act, *h_dhj, *h_dout, *d_fsum;      // model head
   float *d_pre, *negdz, *d_act3, *d_wout, *d_ri, *d_w1f, *dlr, *d_act[2], *d_G, *d_Gp;   // block (reused)
+  float *dlrT, *inT, *wsT;   // K-major operands of the tcgen05 backward GEMMs: (2d, R), (d, R), (d, 2d)
   float *d_bc, *d_x0, *d_mul_L, *dAsym, *ddeg, *dA, *dots, *d_key, *d_query;
   float *dgh, *dh[2], *d_xs;
 };
