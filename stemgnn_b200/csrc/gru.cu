@@ -260,29 +260,29 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
       float nx_r = 0.f, nx_z = 0.f, nx_n = 0.f;
       if (s + 1 < N) load_gi(s + 1, b0 + g * G + fb, bvalid[g], nx_r, nx_z, nx_n);
 
-      // (a) this lane's k-slice of h_{s-1} for the G sequences: k' = 128*j + 4*lane + {0..3}
-      float4 h[G][JC];
-#pragma unroll
-      for (int bb = 0; bb < G; ++bb)
-#pragma unroll
-        for (int j = 0; j < JC; ++j)
-          h[bb][j] = *reinterpret_cast<const float4*>(hb_cur + bb * KP + 128 * j + 4 * lane);
-
-      // (b) mat-vec: each W_hh element is read from shared memory once per group-step (32 lanes x 16 B
-      //     distinct per LDS.128) and used for the G sequences; two partial sums per (row, sequence)
+      // (a)+(b) mat-vec, k-chunk outer / row inner: the lane's slice of h_{s-1} (k' = 128 j + 4 lane + {0..3}
+      //     for the G sequences) is loaded chunk by chunk so that the loads of chunk j+1 overlap the FFMA2s of
+      //     chunk j.  Each W_hh element is read from shared memory once per group-step (32 lanes x 16 B distinct
+      //     per LDS.128) and used for the G sequences; two partial sums per (row, sequence).
       float2 acc[ROWS][G];
-      const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * lane;
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
+      for (int r = 0; r < ROWS; ++r)
 #pragma unroll
         for (int bb = 0; bb < G; ++bb) acc[r][bb] = make_float2(0.f, 0.f);
+      const float* wbase = Wsm + (long long)(w * ROWS) * KP + 4 * lane;
 #pragma unroll
-        for (int j = 0; j < JC; ++j) {
+      for (int j = 0; j < JC; ++j) {
+        float4 h[G];
+#pragma unroll
+        for (int bb = 0; bb < G; ++bb)
+          h[bb] = *reinterpret_cast<const float4*>(hb_cur + bb * KP + 128 * j + 4 * lane);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
           const float4 wv = *reinterpret_cast<const float4*>(wbase + r * KP + 128 * j);
 #pragma unroll
           for (int bb = 0; bb < G; ++bb) {
-            acc[r][bb] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[bb][j].x, h[bb][j].y), acc[r][bb]);
-            acc[r][bb] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[bb][j].z, h[bb][j].w), acc[r][bb]);
+            acc[r][bb] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[bb].x, h[bb].y), acc[r][bb]);
+            acc[r][bb] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[bb].z, h[bb].w), acc[r][bb]);
           }
         }
       }

@@ -305,3 +305,28 @@ def test_folded_weight_cache_is_invalidated_by_parameter_updates():
         f_ref, _ = tp.model_forward(x, p)
     assert not torch.equal(f1, f3)
     assert_close(f3, f_ref, msg="forward after in-place weight update")
+
+
+@pytest.mark.parametrize("B,N,W,H,multi", [(6, 25, 28, 28, 5), (1, 5, 12, 1, 5), (2, 17, 4, 2, 3), (5, 130, 12, 3, 1)])
+def test_unusual_shapes_forward_and_backward_vs_port(B, N, W, H, multi):
+    """COVID-19 config of the reference README (W=28, H=28: d=560 exceeds the tensor-core tile, fp32 path),
+    single-window batches, tiny graphs, multi_layer=1 — forward and every gradient against the port."""
+    c = dict(B=B, N=N, W=W, H=H, multi=multi, pseed=900 + N, mode="trained")
+    p = case_params(c)
+    m = build_model(c, DEV, p).eval()
+    x, y = tp.synthetic_batch(B, N, W, H, seed=5)
+    xd = x.to(DEV)
+    f, a = m(xd)
+    torch.nn.functional.mse_loss(f, y.to(DEV) if H > 1 else y.to(DEV)).backward()
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    f_ref, a_ref = tp.model_forward(x, pr)
+    torch.nn.functional.mse_loss(f_ref, y).backward()
+    assert_close(f, f_ref, msg="forecast")
+    assert_close(a, a_ref, msg="attention")
+    named = dict(m.named_parameters())
+    for k, v in pr.items():
+        if v.grad is None:
+            continue
+        g, r = named[k].grad.cpu(), v.grad
+        scale = max(float(r.abs().max()), 1e-12)
+        assert float((g - r).abs().max()) <= 1e-2 * scale + 1e-9, f"{k}: grad mismatch"
