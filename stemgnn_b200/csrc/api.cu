@@ -43,6 +43,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
   ws.attention = take(N * N);
   ws.gru_scratch = take(2 * R);
   ws.gi = take(N * R * 3);
+  ws.skbuf = take(8 * (N * N > 3 * N * B * W ? N * N : 3 * N * B * W));
   ws.row_m = training ? take(R) : nullptr;
   ws.row_zinv = training ? take(R) : nullptr;
   ws.h_all = training ? take(N * R) : nullptr;
@@ -175,11 +176,11 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
 // StockBlockLayer.forward (base_model.py:61-75)
 int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int stack_idx,
                   int gemm_mode, int reuse_folded, const float* x_bnw, const float* x_bwn,
-                  const float* mul_L, const BlockWs& b, cudaStream_t st) {
+                  const float* mul_L, const BlockWs& b, float* skbuf, cudaStream_t st) {
   const int B = dm.B, N = dm.N, W = dm.W, T = dm.multi * W, d = 4 * T, R = B * N;
   const int PW = (stack_idx == 0) ? T + W : T;
   if (!reuse_folded) SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
-  SG_TRY(launch_gft(mul_L, x_bwn, b.G, B, N, W, st));
+  SG_TRY(launch_gft(mul_L, x_bwn, b.G, skbuf, B, N, W, st));
   SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st));
   {   // pre = [real3 | imag3] @ woutT^T : tcgen05 TF32 unless exact fp32 is requested
     int rc = -1;
@@ -219,6 +220,16 @@ static int check_block_params(const stemgnn_block_params_t* bp, int stack_idx) {
   return 0;
 }
 
+// C[i] = alpha * sum_z P[z][i] + beta * Cin[i]   (fixed summation order)
+__global__ void splitk_reduce_kernel(const float* __restrict__ P, int ks, int n, float alpha,
+                                     const float* __restrict__ Cin, float beta, float* __restrict__ C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int z = 0; z < ks; ++z) acc += P[(long long)z * n + i];
+  C[i] = alpha * acc + (Cin != nullptr ? beta * Cin[i] : 0.f);
+}
+
 int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const float* key,
                   const float* query, float* attention, const Workspace& ws, cudaStream_t st) {
   const int B = dm.B, N = dm.N;
@@ -233,15 +244,24 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
   SG_TRY(launch_attention(a, ws.qmax, st));
   SG_TRY(launch_laplacian(ws.a_raw, ws.deg, attention, ws.mul_L, N, st));
   const size_t nn = (size_t)N * N;
-  {   // third = 2 L L   (base_model.py:131; first_laplacian is zero)
-    GemmOperands g = {ws.mul_L + nn, N, 0, ws.mul_L + nn, N, 0, nullptr, N, N, N};
-    EpiAxpby epi = {ws.mul_L + 2 * nn, N, 0, nullptr, 0, 0, 2.f, 0.f};
-    SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb2")));
-  }
-  {   // forth = 2 L third - L   (base_model.py:132)
-    GemmOperands g = {ws.mul_L + nn, N, 0, ws.mul_L + 2 * nn, N, 0, nullptr, N, N, N};
-    EpiAxpby epi = {ws.mul_L + 3 * nn, N, 0, ws.mul_L + nn, N, 0, 2.f, -1.f};
-    SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb3")));
+  // the two N^3 Chebyshev products fill only a few CTAs: deterministic split-K (partials + ordered reduce)
+  const int ks = pick_ksplit(N, N, N);
+  for (int term = 2; term <= 3; ++term) {
+    // term 2: third = 2 L L (base_model.py:131; first_laplacian is zero); term 3: forth = 2 L third - L (:132)
+    const float* Bm = ws.mul_L + (size_t)(term - 1) * nn;
+    float* Cm = ws.mul_L + (size_t)term * nn;
+    const float* Cin = term == 3 ? ws.mul_L + nn : nullptr;
+    if (ks > 1 && ks <= 8) {
+      GemmOperands g = {ws.mul_L + nn, N, 0, Bm, N, 0, nullptr, N, N, N, ks};
+      EpiPartial epi = {ws.skbuf, N, (long long)nn};
+      SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb_splitk")));
+      splitk_reduce_kernel<<<ceil_div((int)nn, 256), 256, 0, st>>>(ws.skbuf, ks, (int)nn, 2.f, Cin, -1.f, Cm);
+      SG_LAUNCH_CHECK("splitk_reduce_kernel");
+    } else {
+      GemmOperands g = {ws.mul_L + nn, N, 0, Bm, N, 0, nullptr, N, N, N};
+      EpiAxpby epi = {Cm, N, 0, Cin, N, 0, 2.f, Cin != nullptr ? -1.f : 0.f};
+      SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb")));
+    }
   }
   return 0;
 }
@@ -297,9 +317,9 @@ int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
   SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
   SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
   SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, opts->reuse_folded && !opts->training, ws.x_bnw, x,
-                       ws.mul_L, ws.blk[0], st));
+                       ws.mul_L, ws.blk[0], ws.skbuf, st));
   SG_TRY(block_forward(dm, p->block[1], 1, opts->gemm_mode, opts->reuse_folded && !opts->training,
-                       ws.blk[0].bc_bnw, ws.blk[0].bc_bwn, ws.mul_L, ws.blk[1], st));
+                       ws.blk[0].bc_bnw, ws.blk[0].bc_bwn, ws.mul_L, ws.blk[1], ws.skbuf, st));
   SG_TRY(launch_model_head(ws.blk[0].forecast, ws.blk[1].forecast, p->fc0_w, p->fc0_b, p->fc2_w,
                            p->fc2_b, forecast, dm.B, dm.N, dm.W, dm.H, st));
   if (mul_L != nullptr)
@@ -369,7 +389,7 @@ int stemgnn_block_forward(const stemgnn_dims_t* dims, const stemgnn_block_params
   float* x_bwn = ws.blk[1 - stack_idx].bc_bwn;   // scratch from the other block's slot
   bnw_to_bwn_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x_bnw, x_bwn, dims->B, dims->N, dims->W);
   SG_LAUNCH_CHECK("bnw_to_bwn_kernel");
-  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, 0, x_bnw, x_bwn, mul_L, b, st));
+  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, 0, x_bnw, x_bwn, mul_L, b, ws.skbuf, st));
   SG_CUDA(cudaMemcpyAsync(forecast, b.forecast, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (stack_idx == 0)
     SG_CUDA(cudaMemcpyAsync(backcast, b.bc_bnw, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));

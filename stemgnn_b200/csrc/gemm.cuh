@@ -274,6 +274,15 @@ struct EpiAtomicAdd {
   }
 };
 
+// deterministic split-K: split z writes its partial product to P[z] (M x ldp); a fixed-order reduction
+// kernel combines them afterwards (bitwise reproducible, unlike atomics)
+struct EpiPartial {
+  float* P; int ldp; long long stride;
+  __device__ __forceinline__ void store4(int, int m, int n, int valid, float4 v, float4) const {
+    st4_guard(P + (long long)blockIdx.z * stride, (long long)m * ldp + n, valid, v);
+  }
+};
+
 // number of K-splits that brings a (M x N x K) product to about two waves of CTAs
 inline int pick_ksplit(int M, int N, int K) {
   const int tiles = ceil_div(M, GM_BM) * ceil_div(N, GM_BN);

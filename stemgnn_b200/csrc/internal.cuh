@@ -60,7 +60,8 @@ struct HeadArgs {
   float* save_fs;              // (R, T) or null (training)
   int R, N, T, W;
 };
-int launch_gft(const float* mul_L, const float* x_bwn, float* G, int B, int N, int W, cudaStream_t st);
+int launch_gft(const float* mul_L, const float* x_bwn, float* G, float* skbuf, int B, int N, int W,
+               cudaStream_t st);
 int launch_block_head(const HeadArgs& a, cudaStream_t st);
 int launch_model_head(const float* f0, const float* f1, const float* w0, const float* b0,
                       const float* w2, const float* b2, float* out, int B, int N, int W, int H,
@@ -108,6 +109,7 @@ struct BwdWs {
 };
 struct Workspace {
   float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
+  float* skbuf;    // split-K partial products (8 x max(N*N, 3N*B*W) floats)
   float *row_m, *row_zinv, *h_all, *g_r, *g_z, *g_n, *g_hn;
   BwdWs bwd;
   BlockWs blk[STEMGNN_MAX_STACK];

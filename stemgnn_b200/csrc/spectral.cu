@@ -61,7 +61,7 @@ __global__ void irfft_table_kernel(float* __restrict__ ic, int T) {
 // GEMM rows m = k'*N + n (k' = 0..2 -> Chebyshev terms 1..3), cols c = b*W + t.
 // Destination: G[(b*N + n) * 3W + k'*W + t]  (row-major (B*N) x 3W activation for the GLU chain).
 struct EpiGftScatter {
-  float* G; int N, W;
+  float* G; int N, W; int atomic;    // atomic = 1: split-K partial sums are added into a zeroed G
   __device__ __forceinline__ void store4(int, int m, int n, int valid, float4 v, float4) const {
     const int kp = m / N, node = m - kp * N;
     const float vals[4] = {v.x, v.y, v.z, v.w};
@@ -69,16 +69,46 @@ struct EpiGftScatter {
     for (int j = 0; j < 4; ++j) {
       if (j < valid) {
         const int c = n + j, b = c / W, t = c - b * W;
-        G[((long long)b * N + node) * (3 * W) + kp * W + t] = vals[j];
+        float* dst = G + ((long long)b * N + node) * (3 * W) + kp * W + t;
+        if (atomic) atomicAdd(dst, vals[j]);
+        else *dst = vals[j];
       }
     }
   }
 };
 
-int launch_gft(const float* mul_L, const float* x_bwn, float* G, int B, int N, int W, cudaStream_t st) {
+// G[(b*N + n)*3W + k'*W + t] = sum_z P[z][(k'*N + n)*(B*W) + b*W + t]
+__global__ void gft_reduce_scatter_kernel(const float* __restrict__ P, int ks, float* __restrict__ G, int B, int N,
+                                          int W) {
+  const long long total = (long long)B * N * 3 * W;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int t = (int)(idx % W), kp = (int)((idx / W) % 3);
+  const long long bn = idx / (3 * W);
+  const int n = (int)(bn % N), b = (int)(bn / N);
+  const long long src = ((long long)kp * N + n) * ((long long)B * W) + (long long)b * W + t;
+  const long long stride = (long long)3 * N * B * W;
+  float acc = 0.f;
+  for (int z = 0; z < ks; ++z) acc += P[(long long)z * stride + src];
+  G[idx] = acc;
+}
+
+int launch_gft(const float* mul_L, const float* x_bwn, float* G, float* skbuf, int B, int N, int W,
+               cudaStream_t st) {
   // A = mul_L[1..3] viewed as (3N x N); B operand = x (B*W x N) read as B[n*ldb + k]
+  // (3N x N) . (N x B*W) fills only ~54 CTAs: deterministic split-K (partials + fixed-order reduction)
+  const int ks = skbuf != nullptr ? pick_ksplit(3 * N, B * W, N) : 1;
+  if (ks > 1 && ks <= 8) {      // skbuf holds 8 partial products
+    GemmOperands g = {mul_L + (long long)N * N, N, 0, x_bwn, N, 0, nullptr, 3 * N, B * W, N, ks};
+    EpiPartial epi = {skbuf, B * W, (long long)3 * N * B * W};
+    SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "gft_gemm_splitk")));
+    const long long total = (long long)B * N * 3 * W;
+    gft_reduce_scatter_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(skbuf, ks, G, B, N, W);
+    SG_LAUNCH_CHECK("gft_reduce_scatter_kernel");
+    return 0;
+  }
   GemmOperands g = {mul_L + (long long)N * N, N, 0, x_bwn, N, 0, nullptr, 3 * N, B * W, N};
-  EpiGftScatter epi = {G, N, W};
+  EpiGftScatter epi = {G, N, W, 0};
   return launch_sgemm<false, true, false>(g, epi, 1, st, "gft_gemm");
 }
 
