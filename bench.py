@@ -286,7 +286,11 @@ def run_ours(args, rank, world, local_rank):
         ach = gru_flops / (gru_ms * 1e-3) / 1e12
         roof = {"kernel": "gru_cluster_kernel (GRU recurrence, fp32 FFMA2, 16-CTA clusters)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                # (profiles/r01_ncu_gru_cluster_v3_raw.csv): 50.79 MB + 0.04 MB; algorithmic: the 49.2 MB input
+                # projection it streams + 1.5 MB of W_hh per cluster wave
+                "traffic": 50.83e6, "traffic_unit": "bytes/launch", "peak_source": peak_src,
                 "ms_per_launch": gru_ms, "share_of_step": gru_ms / (dev_ms / args.steps),
                 "note": "latency-bound recurrence: 358 dependent steps; flops = 6BN^3 + 12BN^2"}
     cpu_steps = 15
