@@ -16,6 +16,7 @@
 // Operand precision: fp32 bit patterns are fed directly; kind::tf32 reads the top 19 bits
 // (truncation).  Error budget vs the fp32 reference: DESIGN.md "Precision".
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.cuh"
@@ -60,6 +61,28 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// TMA load multicast to every CTA of `mask` (same CTA-relative smem offset and mbarrier in each)
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -110,6 +133,10 @@ struct GluTcArgs {
   int M, N, K;
 };
 
+// CSZ = 2: CTA pairs (thread-block cluster of 2) share the weight tiles — each CTA fetches half of the rows of
+// Wl / Wr per stage and TMA-multicasts them into both CTAs' shared memory, halving the L2 -> SM weight traffic
+// that bounds this kernel (every CTA needs all 2*N*K weights for its 128 rows).
+template <int CSZ>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wl,
               const __grid_constant__ CUtensorMap map_wr, GluTcArgs g) {
@@ -123,15 +150,19 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bl = reinterpret_cast<float*>(tmem_slot + 2);     // [N] biases staged once per CTA (the epilogue
+  float* s_br = s_bl + N;                                    //  would otherwise stall on 2N global loads per row)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
   const int num_kb = (g.K + TC_BK - 1) / TC_BK;
 
+  const uint32_t crank = CSZ > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CSZ);       // a stage is free once EVERY CTA of the cluster has consumed it
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,6 +178,7 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CSZ > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -159,8 +191,15 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
         tma_load_2d(st, &map_a, &full_bar[s], kb * TC_BK, m0);
-        tma_load_2d(st + a_bytes, &map_wl, &full_bar[s], kb * TC_BK, 0);
-        tma_load_2d(st + a_bytes + w_bytes, &map_wr, &full_bar[s], kb * TC_BK, 0);
+        if (CSZ == 1) {
+          tma_load_2d(st + a_bytes, &map_wl, &full_bar[s], kb * TC_BK, 0);
+          tma_load_2d(st + a_bytes + w_bytes, &map_wr, &full_bar[s], kb * TC_BK, 0);
+        } else {         // this CTA's share of the weight rows, delivered to every CTA of the cluster
+          const int rows = N / CSZ;
+          const uint32_t off = crank * (uint32_t)rows * 128u;
+          tma_load_2d_mc(st + a_bytes + off, &map_wl, &full_bar[s], kb * TC_BK, (int)crank * rows, kMask);
+          tma_load_2d_mc(st + a_bytes + w_bytes + off, &map_wr, &full_bar[s], kb * TC_BK, (int)crank * rows, kMask);
+        }
       }
     }
   } else if (warp == 1) {
@@ -180,11 +219,17 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           umma_tf32(tmem_base, ad, umma_desc_sw128(wl_addr + kk * 32), idesc, acc);
           umma_tf32(tmem_base + TC_RIGHT_COL, ad, umma_desc_sw128(wr_addr + kk * 32), idesc, acc);
         }
-        umma_commit(&empty_bar[s]);                 // stage reusable once these MMAs have read it
+        if (CSZ == 1) umma_commit(&empty_bar[s]);   // stage reusable once these MMAs have read it
+        else umma_commit_mc(&empty_bar[s], kMask);  //   (signalled in every CTA that multicasts into it)
       }
       umma_commit(tmem_full_bar);                   // accumulators complete
     }
   } else {             // ===== epilogue: warps 2..5 =====
+    for (int i = threadIdx.x - 64; i < N; i += 128) {        // overlaps with the MMA main loop
+      s_bl[i] = __ldg(g.bl + i);
+      s_br[i] = __ldg(g.br + i);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");           // epilogue warps only
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
@@ -199,8 +244,8 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          l[j] += __ldg(g.bl + c + j);
-          r[j] = __fdividef(1.0f, 1.0f + __expf(-(r[j] + __ldg(g.br + c + j))));
+          l[j] += s_bl[c + j];
+          r[j] = __fdividef(1.0f, 1.0f + __expf(-(r[j] + s_br[c + j])));
           o[j] = l[j] * r[j];
         }
         float4* po = reinterpret_cast<float4*>(g.out + (size_t)row * g.ldo + c);
@@ -394,25 +439,44 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
     return -1;
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return -1;
+  // CTA pairs with multicast weights unless disabled (STEMGNN_GLU_NO_MULTICAST) or N/2 breaks the 8-row atom
+  static const bool no_mc = getenv("STEMGNN_GLU_NO_MULTICAST") != nullptr;
+  const int csz = (!no_mc && (N % 16 == 0)) ? 2 : 1;
   CUtensorMap ma, ml, mr;
-  if (!make_map(enc, &ma, A, M, K, lda, TC_BM) || !make_map(enc, &ml, Wl, N, K, K, N) ||
-      !make_map(enc, &mr, Wr, N, K, K, N))
+  if (!make_map(enc, &ma, A, M, K, lda, TC_BM) || !make_map(enc, &ml, Wl, N, K, K, N / csz) ||
+      !make_map(enc, &mr, Wr, N, K, K, N / csz))
     return -1;
-  const size_t smem = (size_t)TC_STAGES * (TC_BM * 128 + 2 * (size_t)N * 128) + 64 + 1024;
+  const size_t smem = (size_t)TC_STAGES * (TC_BM * 128 + 2 * (size_t)N * 128) + 64 + 2 * (size_t)N * sizeof(float) + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   GluTcArgs g = {bl, br, out, ldo, save_l, save_s, lds, M, N, K};
-  glu_tc_kernel<<<ceil_div(M, TC_BM), TC_THREADS, smem, st>>>(ma, ml, mr, g);
-  SG_LAUNCH_CHECK("glu_tc_kernel");
+  const int tiles = ceil_div(M, TC_BM);
+  if (csz == 1) {
+    glu_tc_kernel<1><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
+    SG_LAUNCH_CHECK("glu_tc_kernel");
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((tiles + 1) / 2 * 2);       // an odd tail tile gets an idle partner (all of its rows are OOB)
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2>, ma, ml, mr, g));
+  count_launch();
   return 0;
 }
 
-
-// C (+)= alpha * A[M,K] B[N,K]^T on tcgen05 TF32.  B may have fewer than N rows (n_rows_b): the missing
-// rows are TMA zero fill and n_store limits the written columns.  Returns -1 when the shape is unsupported.
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
             float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st) {
   if (N % 16 != 0 || N < 16 || N > 256 || K < 1 || (lda & 3) != 0 || (ldb & 3) != 0) return -1;
