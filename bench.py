@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 B, N, W, H, MULTI = 32, 358, 12, 3, 5
 WORKLOAD = "synthetic N=358 W=12 H=3 batch=32 fp32 eval forward (BASELINE.json configs[1])"
 METRIC = "forecast-windows/sec (B,N,W)=(32,358,12)"
+FORWARD_FLOPS = 28140101688      # SURVEY.md §8(d) dead-work-free count at (32,358,12,3); = oracle.forward_flops
 
 
 def _peaks():
@@ -137,7 +138,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from models.base_model import Model
-    from oracle import torch_port as tp           # synthetic weights/inputs + cpu_baseline leg only
+    from stemgnn_b200 import synthetic as tp      # seeded weights / inputs (plain data generators)
     from stemgnn_b200 import _lib
 
     if not torch.cuda.is_available():
@@ -178,6 +179,23 @@ def run_ours(args, rank, world, local_rank):
         launches = lib.stemgnn_launch_count() - launches0
         clocks = sampler.stop() if sampler else None
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+        # ---- same forward with every GEMM forced to exact fp32 FFMA2 (Model.gemm_mode = 1) ---------------
+        from stemgnn_b200 import runtime as _rt
+        model.gemm_mode = _rt.GEMM_FP32
+        for _ in range(3):
+            model(x_dev)
+        ev32 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                for _ in range(min(args.steps, 20))]
+        for a0, a1 in ev32:
+            flush.zero_()
+            a0.record()
+            model(x_dev)
+            a1.record()
+        torch.cuda.synchronize()
+        fp32_ms = sum(a0.elapsed_time(a1) for a0, a1 in ev32) / len(ev32)
+        model.gemm_mode = _rt.GEMM_AUTO
+        model(x_dev)
 
         # ---- dominant kernel (GRU recurrence) with CUDA events on the launching stream --------------
         gru_ms = None
@@ -295,15 +313,18 @@ def run_ours(args, rank, world, local_rank):
                 "note": "latency-bound recurrence: 358 dependent steps; flops = 6BN^3 + 12BN^2"}
     cpu_steps = 15
     cpu_v, cpu_ms, threads = cpu_reference_forward(cpu_steps, 2)
-    import oracle.stemgnn_oracle as so
     value = world * B * args.steps / (dev_ms * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (GLU chain + folded output map: tf32 tensor-core operands, fp32 accumulate; see exact_fp32)",
+            "data": "synthetic",
+            "exact_fp32": {"value": B / (fp32_ms * 1e-3) * world, "unit": "windows/s", "ms_per_step": fp32_ms,
+                           "what": "same forward with every GEMM on the fp32 FFMA2 path (Model.gemm_mode = 1), rank 0"},
             "config": {"workload": WORKLOAD, "B_per_gpu": B, "N": N, "W": W, "H": H, "multi_layer": MULTI,
                        "mode": "eval forward (Model.forward, no_grad)", "parallelism": f"dp{world} replicas",
                        "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-                       "flops_per_step": so.forward_flops(B, N, W, H)},
+                       "flops_per_step": FORWARD_FLOPS},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": B * W * N * 4, "d2h_bytes_per_step": B * H * N * 4,
                     "ms_per_step": e2e_ms / args.steps},
