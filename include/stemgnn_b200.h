@@ -170,6 +170,13 @@ int stemgnn_spe_seq_cell_forward(const stemgnn_dims_t* dims, const stemgnn_block
                                  int gemm_mode, const float* gfted, float* iffted, void* workspace,
                                  size_t workspace_bytes, stemgnn_stream_t stream);
 
+/* Device-resident data path (reference: data_loader/forecast_dataloader.py:56-63, ForecastDataset.__getitem__):
+ * builds one batch of sliding windows from the normalised series kept in HBM.
+ *   series (T,N) fp32;  end_idx (B) int32: exclusive end row `hi` of every input window (x_end_idx);
+ *   x (B,W,N) = series[hi-W : hi];  y (B,H,N) = series[hi : hi+H]. */
+int stemgnn_gather_windows(const float* series, int T, int N, const int32_t* end_idx, int B, int W, int H,
+                           float* x, float* y, stemgnn_stream_t stream);
+
 /* C[M,N] = alpha * A(M,K) * B(K,N) + beta * C  on the library's fp32 FFMA2 GEMM (test hook).
  * a_kmajor: 0 -> A[m*lda+k], 1 -> A[k*lda+m];  b_nk: 1 -> B[n*ldb+k] (nn.Linear weight), 0 -> B[k*ldb+n]. */
 int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int a_kmajor,

@@ -53,13 +53,15 @@ def load_model(model_dir, epoch=None):
 def inference(model, dataloader, device, node_cnt, window_size, horizon):
     """Rolling forecast: the model emits `len_out` steps per call; the window is shifted by the
     prediction until `horizon` steps exist (one call per batch when the model emits the full
-    horizon).  Returns (forecast, target) numpy arrays of shape (count, horizon, node)."""
+    horizon).  Returns (forecast, target) numpy arrays of shape (count, horizon, node).
+    Forecasts and targets stay on the device until the end of the pass (one D2H copy instead of the
+    reference's two per batch, handler.py:60-63); the values are the same."""
     forecasts, targets = [], []
     model.eval()
     with torch.no_grad():
         for inputs, target in dataloader:
             inputs, target = inputs.to(device), target.to(device)
-            steps = np.zeros([inputs.size(0), horizon, node_cnt], dtype=float)
+            steps = torch.zeros(inputs.size(0), horizon, node_cnt, dtype=torch.float64, device=inputs.device)
             done = 0
             while done < horizon:
                 out, _ = model(inputs)
@@ -69,11 +71,11 @@ def inference(model, dataloader, device, node_cnt, window_size, horizon):
                 inputs[:, :window_size - len_out, :] = inputs[:, len_out:window_size, :].clone()
                 inputs[:, window_size - len_out:, :] = out.clone()
                 take = min(horizon - done, len_out)
-                steps[:, done:done + take, :] = out[:, :take, :].detach().cpu().numpy()
+                steps[:, done:done + take, :] = out[:, :take, :].detach()
                 done += take
             forecasts.append(steps)
-            targets.append(target.detach().cpu().numpy())
-    return np.concatenate(forecasts, axis=0), np.concatenate(targets, axis=0)
+            targets.append(target.detach())
+    return torch.cat(forecasts, dim=0).cpu().numpy(), torch.cat(targets, dim=0).cpu().numpy()
 
 
 def validate(model, dataloader, device, normalize_method, statistic, node_cnt, window_size, horizon,
@@ -98,6 +100,16 @@ def validate(model, dataloader, device, normalize_method, statistic, node_cnt, w
         np.savetxt(f'{result_file}/predict_ape.csv', np.abs((pred - truth) / truth), delimiter=",")
     return dict(mae=score[1], mae_node=score_by_node[1], mape=score[0], mape_node=score_by_node[0],
                 rmse=score[2], rmse_node=score_by_node[2])
+
+
+def _make_loader(dataset, batch_size, shuffle, device):
+    """Same batches as the reference's `DataLoader(dataset, batch_size, shuffle=..., drop_last=False,
+    num_workers=0)` (handler.py:135-138, :200-201).  On a CUDA device the windows are gathered in HBM by
+    `stemgnn_b200.data.DeviceWindowLoader` (identical sampler objects, so identical index order)."""
+    if torch.device(device).type == 'cuda' and os.environ.get('STEMGNN_HOST_LOADER') is None:
+        from stemgnn_b200.data import DeviceWindowLoader
+        return DeviceWindowLoader(dataset, batch_size, shuffle=shuffle, drop_last=False, device=device)
+    return torch_data.DataLoader(dataset, batch_size=batch_size, drop_last=False, shuffle=shuffle, num_workers=0)
 
 
 def _norm_statistic(train_data, method):
@@ -130,10 +142,8 @@ def train(train_data, valid_data, args, result_file):
 
     ds_kw = dict(window_size=args.window_size, horizon=args.horizon, normalize_method=args.norm_method,
                  norm_statistic=normalize_statistic)
-    train_loader = torch_data.DataLoader(ForecastDataset(train_data, **ds_kw), batch_size=args.batch_size,
-                                         drop_last=False, shuffle=True, num_workers=0)
-    valid_loader = torch_data.DataLoader(ForecastDataset(valid_data, **ds_kw), batch_size=args.batch_size,
-                                         shuffle=False, num_workers=0)
+    train_loader = _make_loader(ForecastDataset(train_data, **ds_kw), args.batch_size, True, args.device)
+    valid_loader = _make_loader(ForecastDataset(valid_data, **ds_kw), args.batch_size, False, args.device)
     criterion = nn.MSELoss(reduction='mean').to(args.device)
     print(f"Total Trainable Params: {sum(p.numel() for p in model.parameters() if p.requires_grad)}")
 
@@ -177,8 +187,7 @@ def test(test_data, args, result_train_file, result_test_file):
     node_cnt = test_data.shape[1]
     test_set = ForecastDataset(test_data, window_size=args.window_size, horizon=args.horizon,
                                normalize_method=args.norm_method, norm_statistic=normalize_statistic)
-    test_loader = torch_data.DataLoader(test_set, batch_size=args.batch_size, drop_last=False,
-                                        shuffle=False, num_workers=0)
+    test_loader = _make_loader(test_set, args.batch_size, False, args.device)
     m = validate(model, test_loader, args.device, args.norm_method, normalize_statistic, node_cnt,
                  args.window_size, args.horizon, result_file=result_test_file)
     print('Performance on test set: MAPE: {:5.2f} | MAE: {:5.2f} | RMSE: {:5.4f}'.format(

@@ -415,6 +415,35 @@ int stemgnn_spe_seq_cell_forward(const stemgnn_dims_t* dims, const stemgnn_block
   return launch_irfft_rows(b.act3, b.ic, iffted, dims->B, dims->N, T, st);
 }
 
+// x[b][t][n] = series[(end_idx[b] - W + t) * N + n] ;  y[b][h][n] = series[(end_idx[b] + h) * N + n]
+__global__ void gather_windows_kernel(const float* __restrict__ series, int T, int N,
+                                      const int32_t* __restrict__ end_idx, int B, int W, int H,
+                                      float* __restrict__ x, float* __restrict__ y) {
+  const long long per = (long long)(W + H) * N;
+  const long long total = (long long)B * per;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / per);
+    const long long r = idx - (long long)b * per;
+    const int row = (int)(r / N), n = (int)(r % N);
+    const long long src_row = (long long)end_idx[b] - W + row;
+    const float v = (src_row >= 0 && src_row < T) ? series[src_row * N + n] : 0.f;
+    if (row < W) x[((long long)b * W + row) * N + n] = v;
+    else y[((long long)b * H + (row - W)) * N + n] = v;
+  }
+}
+
+int stemgnn_gather_windows(const float* series, int T, int N, const int32_t* end_idx, int B, int W, int H,
+                           float* x, float* y, stemgnn_stream_t stream) {
+  clear_error();
+  SG_CHECK(series && end_idx && x && y && T > 0 && N > 0 && B > 0 && W > 0 && H >= 0, "gather_windows: bad arguments");
+  const long long total = (long long)B * (W + H) * N;
+  const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+  gather_windows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(series, T, N, end_idx, B, W, H, x, y);
+  SG_LAUNCH_CHECK("gather_windows_kernel");
+  return 0;
+}
+
 int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int a_kmajor,
                   const float* B, int ldb, int b_nk, float beta, float* C, int ldc,
                   stemgnn_stream_t stream) {
