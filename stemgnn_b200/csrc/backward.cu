@@ -127,23 +127,6 @@ __global__ void __launch_bounds__(256) block_head_bwd_kernel(HeadBwdArgs a) {
   }
 }
 
-// ---- GLU gate backward: out = l * s, s = sigmoid(r) ----------------------------------------------------------
-// dlr[row][n] = d_out * s ;  dlr[row][N + n] = d_out * l * s * (1 - s)
-__global__ void __launch_bounds__(256) glu_gate_bwd_kernel(const float* __restrict__ d_out, int ldd,
-                                                           const float* __restrict__ l,
-                                                           const float* __restrict__ s, int R, int N,
-                                                           float* __restrict__ dlr) {
-  const long long total = (long long)R * N;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(idx / N), n = (int)(idx % N);
-    const float d = d_out[(long long)row * ldd + n];
-    const float sv = s[idx], lv = l[idx];
-    dlr[(long long)row * 2 * N + n] = d * sv;
-    dlr[(long long)row * 2 * N + N + n] = d * lv * sv * (1.f - sv);
-  }
-}
-
 // out[c*ldo + r] = in[r*ldi + c]   (32x32 shared-memory tiles)
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int rows, int cols, int ldi,
                                                         float* __restrict__ out, int ldo) {

@@ -1,21 +1,25 @@
 // GRU over the node axis + key/query contraction  (reference: models/base_model.py:92,137 and
-// :154-155; gate equations as in torch.nn.GRU, gate order [r,z,n], h0 = 0).
+// :154-155; gate equations as in torch.nn.GRU, gate order [r,z,n], h0 = 0) — forward and BPTT.
 //
 // The recurrence is N dependent steps of h(B x N) . W_hh^T(N x 3N): latency-bound, O(B N^3).
-// B200 design (DESIGN.md "GRU"):
-//   * batch elements are independent sequences -> one THREAD-BLOCK CLUSTER of CS=16 CTAs per
-//     4-5 sequences (7 clusters x 5 sequences = 112 SMs at B=32);
+// B200 design (measurements in profiles/README.md):
+//   * batch elements are independent sequences -> one THREAD-BLOCK CLUSTER of 16 CTAs per 4-5
+//     sequences (7 clusters x 5 sequences = 112 SMs at B=32: a B200 keeps 7 clusters of 16 resident);
 //   * each CTA of a cluster owns ceil(N/16) hidden units: its 3*U rows of W_hh stay resident in
 //     shared memory for all N steps (persistent-RNN), so W_hh is read from HBM exactly once;
-//   * per step: packed-fp32 (FFMA2) mat-vec against the 4 hidden vectors, gate math, then the new
-//     hidden slice is sent to every CTA's next-step buffer through DISTRIBUTED SHARED MEMORY with
-//     st.async stores that signal a per-buffer mbarrier in the destination CTA (no cluster-wide
-//     barrier on the critical path: a CTA starts step s+1 as soon as its 16 slices have landed);
-//     the input projection W_ih x_s + b_ih of all steps is one
-//     parallel GEMM beforehand (gru_input_proj) whose rows are prefetched a step ahead;
-//   * key/query (sum over steps of h_s * w[s]) are accumulated in registers, so the (N,B,N) GRU
-//     output is never materialised in eval mode (it is written only when the backward needs it).
+//   * per step: packed-fp32 (FFMA2) mat-vec in which every W_hh element is read from shared memory
+//     once and used for all sequences of the cluster, recursive-halving warp reduction, gate math,
+//     then the new hidden slice is sent to every CTA's next-step buffer through DISTRIBUTED SHARED
+//     MEMORY with st.async stores that signal a per-buffer mbarrier in the destination CTA (no
+//     cluster-wide barrier on the critical path: a CTA starts step s+1 when its 16 slices landed);
+//   * the input projection W_ih x_s + b_ih of all steps is one GEMM beforehand (gru_input_proj),
+//     prefetched a step ahead; key/query (sum over steps of h_s * w[s]) accumulate in registers, so
+//     the (N,B,N) GRU output is never materialised in eval mode;
+//   * BPTT (gru_bwd_cluster_kernel) reuses the layout: local gate gradients, partial W_hh^T d_gh over
+//     the resident rows, reduce-scatter of the partial sums over DSMEM.
 // A generic per-step-launch path covers N > 512 or devices that refuse the 16-CTA cluster.
+// Variants kept for measurement (opt-in through STEMGNN_GRU_MODE / STEMGNN_GRU_UW): two software-
+// pipelined groups per cluster, unit-wise step; both measured slower (profiles/README.md).
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
