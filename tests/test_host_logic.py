@@ -200,3 +200,36 @@ def test_c_abi_rejects_bad_arguments_without_gpu():
     assert rc != 0 and b"null" in lib.stemgnn_last_error()
     with pytest.raises(RuntimeError, match="stemgnn_b200"):
         _lib.check(rc, "forward")
+
+
+# ---- state_dict checkpoints ---------------------------------------------------------
+def test_state_checkpoint_roundtrip_and_resume(tmp_path):
+    from models import handler
+    from models.base_model import Model
+    from stemgnn_b200 import checkpoint as ck
+    torch.manual_seed(3)
+    m = Model(11, 2, 12, 2, horizon=3)
+    opt = torch.optim.RMSprop(m.parameters(), lr=1e-3, eps=1e-8)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.5)
+    for p in m.parameters():                       # fake one optimiser step on CPU (no forward needed)
+        p.grad = torch.randn_like(p) * 0.01
+    opt.step(); sched.step()
+    path = ck.save_checkpoint(str(tmp_path / "state.pt"), m, opt, sched, epoch=4, extra={"mae": 1.5})
+    m2, c = ck.load_checkpoint(path)                                     # weights_only=True load
+    assert c["epoch"] == 4 and c["extra"]["mae"] == 1.5
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    opt2 = torch.optim.RMSprop(m2.parameters(), lr=1e-3, eps=1e-8)
+    sched2 = torch.optim.lr_scheduler.ExponentialLR(opt2, gamma=0.5)
+    assert ck.restore_training(c, opt2, sched2) == 5
+    assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"] == 5e-4
+    s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
+    assert all(torch.equal(s1[i]["square_avg"], s2[i]["square_avg"]) for i in s1)
+    # reference-style whole-module pickle -> tensor-only checkpoint
+    handler.save_model(m, str(tmp_path), 7)
+    dst = ck.convert_module_pickle(str(tmp_path / "7_stemgnn.pt"), str(tmp_path / "conv.pt"))
+    m3, _ = ck.load_checkpoint(dst)
+    assert torch.equal(m3.GRU.weight_hh_l0, m.GRU.weight_hh_l0)
+    with pytest.raises(RuntimeError):
+        torch.save({"format": "other"}, str(tmp_path / "bad.pt"))
+        ck.load_checkpoint(str(tmp_path / "bad.pt"))
