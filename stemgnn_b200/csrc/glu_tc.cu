@@ -88,6 +88,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// Same for 64-byte rows (16 fp32 along K per stage): SWIZZLE_64B, 8-row groups 512 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                             // layout type SWIZZLE_64B
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);        // start address            bits [0,14)
@@ -136,7 +146,9 @@ struct GluTcArgs {
 // CSZ = 2: CTA pairs (thread-block cluster of 2) share the weight tiles — each CTA fetches half of the rows of
 // Wl / Wr per stage and TMA-multicasts them into both CTAs' shared memory, halving the L2 -> SM weight traffic
 // that bounds this kernel (every CTA needs all 2*N*K weights for its 128 rows).
-template <int CSZ>
+// BK = 32: 128-byte rows, 2 stages of 76 KB;  BK = 16: 64-byte rows, 5 stages of 38 KB (more loads in flight:
+// the main loop is bound by L2 -> SM latency/bandwidth, not by the tensor pipe).
+template <int CSZ, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wl,
               const __grid_constant__ CUtensorMap map_wr, GluTcArgs g) {
@@ -144,23 +156,25 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   // 1024-byte alignment is required by the 128B swizzle pattern
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int N = g.N;
-  const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)N * 128;
+  constexpr int RB = BK * 4;                        // bytes per tile row
+  constexpr int NSTAGE = BK == 32 ? 2 : 5;
+  const uint32_t a_bytes = TC_BM * RB, w_bytes = (uint32_t)N * RB;
   const uint32_t stage_bytes = a_bytes + 2 * w_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
-  uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * stage_bytes);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tmem_full_bar = empty_bar + NSTAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* s_bl = reinterpret_cast<float*>(tmem_slot + 2);     // [N] biases staged once per CTA (the epilogue
   float* s_br = s_bl + N;                                    //  would otherwise stall on 2N global loads per row)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
-  const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+  const int num_kb = (g.K + BK - 1) / BK;
 
   const uint32_t crank = CSZ > 1 ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CSZ);       // a stage is free once EVERY CTA of the cluster has consumed it
     }
@@ -185,20 +199,20 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        const int s = kb % NSTAGE;
+        const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_2d(st, &map_a, &full_bar[s], kb * TC_BK, m0);
+        tma_load_2d(st, &map_a, &full_bar[s], kb * BK, m0);
         if (CSZ == 1) {
-          tma_load_2d(st + a_bytes, &map_wl, &full_bar[s], kb * TC_BK, 0);
-          tma_load_2d(st + a_bytes + w_bytes, &map_wr, &full_bar[s], kb * TC_BK, 0);
+          tma_load_2d(st + a_bytes, &map_wl, &full_bar[s], kb * BK, 0);
+          tma_load_2d(st + a_bytes + w_bytes, &map_wr, &full_bar[s], kb * BK, 0);
         } else {         // this CTA's share of the weight rows, delivered to every CTA of the cluster
           const int rows = N / CSZ;
-          const uint32_t off = crank * (uint32_t)rows * 128u;
-          tma_load_2d_mc(st + a_bytes + off, &map_wl, &full_bar[s], kb * TC_BK, (int)crank * rows, kMask);
-          tma_load_2d_mc(st + a_bytes + w_bytes + off, &map_wr, &full_bar[s], kb * TC_BK, (int)crank * rows, kMask);
+          const uint32_t off = crank * (uint32_t)rows * (uint32_t)RB;
+          tma_load_2d_mc(st + a_bytes + off, &map_wl, &full_bar[s], kb * BK, (int)crank * rows, kMask);
+          tma_load_2d_mc(st + a_bytes + w_bytes + off, &map_wr, &full_bar[s], kb * BK, (int)crank * rows, kMask);
         }
       }
     }
@@ -206,18 +220,20 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (lane == 0) {   // ===== MMA issuer =====
       const uint32_t idesc = umma_idesc_tf32(N);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        const int s = kb % NSTAGE;
+        const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t wl_addr = a_addr + a_bytes, wr_addr = wl_addr + w_bytes;
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; ++kk) {   // 8 tf32 = 32 bytes along K per instruction
-          const uint64_t ad = umma_desc_sw128(a_addr + kk * 32);
+        for (int kk = 0; kk < BK / 8; ++kk) {   // 8 tf32 = 32 bytes along K per instruction
+          const uint64_t ad = BK == 32 ? umma_desc_sw128(a_addr + kk * 32) : umma_desc_sw64(a_addr + kk * 32);
           const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-          umma_tf32(tmem_base, ad, umma_desc_sw128(wl_addr + kk * 32), idesc, acc);
-          umma_tf32(tmem_base + TC_RIGHT_COL, ad, umma_desc_sw128(wr_addr + kk * 32), idesc, acc);
+          const uint64_t dl = BK == 32 ? umma_desc_sw128(wl_addr + kk * 32) : umma_desc_sw64(wl_addr + kk * 32);
+          const uint64_t dr = BK == 32 ? umma_desc_sw128(wr_addr + kk * 32) : umma_desc_sw64(wr_addr + kk * 32);
+          umma_tf32(tmem_base, ad, dl, idesc, acc);
+          umma_tf32(tmem_base + TC_RIGHT_COL, ad, dr, idesc, acc);
         }
         if (CSZ == 1) umma_commit(&empty_bar[s]);   // stage reusable once these MMAs have read it
         else umma_commit_mc(&empty_bar[s], kMask);  //   (signalled in every CTA that multicasts into it)
@@ -412,13 +428,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor (rows x cols, row stride ld elements), box = box_rows x 32 cols, 128B swizzle
-bool make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+bool make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows,
+              int bk = TC_BK) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -442,21 +460,29 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   // CTA pairs with multicast weights unless disabled (STEMGNN_GLU_NO_MULTICAST) or N/2 breaks the 8-row atom
   static const bool no_mc = getenv("STEMGNN_GLU_NO_MULTICAST") != nullptr;
   const int csz = (!no_mc && (N % 16 == 0)) ? 2 : 1;
+  static const bool bk16 = getenv("STEMGNN_GLU_BK16") != nullptr;
+  const int bk = bk16 ? 16 : 32;
+  const int nstage = bk == 32 ? 2 : 5;
   CUtensorMap ma, ml, mr;
-  if (!make_map(enc, &ma, A, M, K, lda, TC_BM) || !make_map(enc, &ml, Wl, N, K, K, N / csz) ||
-      !make_map(enc, &mr, Wr, N, K, K, N / csz))
+  if (!make_map(enc, &ma, A, M, K, lda, TC_BM, bk) || !make_map(enc, &ml, Wl, N, K, K, N / csz, bk) ||
+      !make_map(enc, &mr, Wr, N, K, K, N / csz, bk))
     return -1;
-  const size_t smem = (size_t)TC_STAGES * (TC_BM * 128 + 2 * (size_t)N * 128) + 64 + 2 * (size_t)N * sizeof(float) + 1024;
+  const size_t smem = (size_t)nstage * ((size_t)TC_BM * bk * 4 + 2 * (size_t)N * bk * 4) + 128 +
+                      2 * (size_t)N * sizeof(float) + 1024;
+  if (smem > 227 * 1024) return -1;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   GluTcArgs g = {bl, br, out, ldo, save_l, save_s, lds, M, N, K};
   const int tiles = ceil_div(M, TC_BM);
   if (csz == 1) {
-    glu_tc_kernel<1><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
+    if (bk == 32) glu_tc_kernel<1, 32><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
+    else glu_tc_kernel<1, 16><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
     SG_LAUNCH_CHECK("glu_tc_kernel");
     return 0;
   }
@@ -472,7 +498,8 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2>, ma, ml, mr, g));
+  if (bk == 32) SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2, 32>, ma, ml, mr, g));
+  else SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2, 16>, ma, ml, mr, g));
   count_launch();
   return 0;
 }
