@@ -225,6 +225,8 @@ class Model(nn.Module):
             seed, offset = 0, 0
             if use_dropout and dropout_mask is None:
                 seed = int(torch.initial_seed()) ^ 0x5DEECE66D
+                rank = (getattr(self, "_ddp", None) or {}).get("rank", 0)
+                seed = (seed + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF    # replicas draw different masks
                 self._dropout_calls += 1
                 offset = self._dropout_calls * ((x.shape[0] * self.unit * self.unit + 3) // 4 + 1)
             mask = None

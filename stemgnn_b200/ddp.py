@@ -57,7 +57,8 @@ def broadcast_parameters(module, src=0, group=None):
 def attach(model, group=None):
     """Marks a stemgnn_b200 Model for data-parallel training: its backward all-reduces the flat
     gradient buffer before handing gradients to autograd."""
-    model._ddp = {"group": group, "enabled": world_size(group) > 1}
+    ws = world_size(group)
+    model._ddp = {"group": group, "enabled": ws > 1, "rank": dist.get_rank(group) if ws > 1 else 0}
     broadcast_parameters(model, 0, group)
     return model
 
