@@ -85,6 +85,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
     w.dAsym = take(N * N); w.ddeg = take(N); w.dA = take(N * N);
     w.dots = take(R); w.d_key = take(R); w.d_query = take(R);
     w.dgh = take(N * R * 3); w.dh[0] = take(R); w.dh[1] = take(R); w.d_xs = take(N * B * W);
+    w.dghT = take(3 * N * (N * B + 4)); w.hT = take(N * (N * B + 4));
   }
   ws.floats = off;
   return ws;

@@ -709,8 +709,28 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
   const float* dgi = ws.gi;
   const int SB = N * B;
   //   dW_hh += DGH[1:]^T h_all[:-1] ;  db_hh += colsum(DGH)
-  SG_TRY((gemm_acc<true, false>(st, 3 * N, N, SB - B, dgh + (size_t)B * 3 * N, 3 * N, ws.h_all, N, gr.gru_w_hh, N,
-                                "d_gru_w_hh")));
+  {
+    const int Kr = SB - B;                      // step 0 has h_{-1} = 0
+    int rc = -1;
+    if (opts->gemm_mode != 1 && gr.gru_w_hh != nullptr && Kr > 0) {
+      // tcgen05 TF32: both operands made K-major by one transpose each, output columns in chunks of <= 256
+      const int ldT = (Kr + 3) / 4 * 4;
+      SG_TRY(transpose(st, dgh + (size_t)B * 3 * N, Kr, 3 * N, 3 * N, w.dghT, ldT));
+      SG_TRY(transpose(st, ws.h_all, Kr, N, N, w.hT, ldT));
+      rc = 0;
+      for (int n0 = 0; n0 < N && rc == 0; n0 += 256) {
+        const int nn_ = N - n0 < 256 ? N - n0 : 256;
+        const int npad = (nn_ + 15) / 16 * 16;
+        rc = tc_gemm(3 * N, npad, Kr, 1.f, w.dghT, ldT, w.hT + (size_t)n0 * ldT, ldT, nn_, gr.gru_w_hh + n0, nullptr,
+                     0, N, nn_, 1, 8, st);
+        if (rc > 0) return rc;
+      }
+      SG_CHECK(rc == 0 || rc == -1, "tc dW_hh");
+    }
+    if (rc < 0)
+      SG_TRY((gemm_acc<true, false>(st, 3 * N, N, Kr, dgh + (size_t)B * 3 * N, 3 * N, ws.h_all, N, gr.gru_w_hh, N,
+                                    "d_gru_w_hh")));
+  }
   SG_TRY(colsum_acc(st, dgh, SB, 3 * N, 3 * N, 1.f, gr.gru_b_hh));
   //   dW_ih += DGI^T xs ;  db_ih += colsum(DGI) ;  d_xs = DGI W_ih
   SG_TRY((gemm_acc<true, false>(st, 3 * N, W, SB, dgi, 3 * N, ws.xs, W, gr.gru_w_ih, W, "d_gru_w_ih")));

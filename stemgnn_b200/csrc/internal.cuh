@@ -106,6 +106,7 @@ struct BwdWs {
   float *dlrT, *inT, *wsT;   // K-major operands of the tcgen05 backward GEMMs: (2d, R), (d, R), (d, 2d)
   float *d_bc, *d_x0, *d_mul_L, *dAsym, *ddeg, *dA, *dots, *d_key, *d_query;
   float *dgh, *dh[2], *d_xs;
+  float *dghT, *hT;          // (3N, S*B) and (N, S*B): K-major operands of the tensor-core dW_hh GEMM
 };
 struct Workspace {
   float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
