@@ -43,46 +43,60 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region.  NVML is polled from a background thread
+    every ~2 ms (the timed region is only tens of milliseconds long, too short for `nvidia-smi -lms`); falls back
+    to one nvidia-smi query when pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
-        self.p = None
+        import threading
+        self.index, self.samples, self.reason_bits, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
-                                      stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indices follow the physical order; honour CUDA_VISIBLE_DEVICES when it lists integers
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self._nv = None
+
+    def _poll(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            sm = sorted(self.samples)
+            reasons = sorted(k for k, bit in self.REASONS.items() if self.reason_bits & bit)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml polled every 2 ms inside the timed region"}
         try:
-            out = self.p.communicate(timeout=5)[0]
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+            f = [v.strip() for v in out.strip().split(",")]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": [], "samples": 1,
+                    "source": "nvidia-smi, one query right after the timed region"}
         except Exception:
-            out = ""
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [v.strip() for v in line.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
 
 
 def cpu_reference_forward(steps, warmup):
