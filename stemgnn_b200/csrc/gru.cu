@@ -1017,10 +1017,48 @@ __global__ void __launch_bounds__(128) gru_step_kernel(GruArgs a, int s, const f
   }
 }
 
-// gi[(s*B+b)][g*N+u] = W_i{g} x_s[b] + b_i{g}   for all steps at once: (N*B x W) . (W x 3N)
+// gi[(s*B+b)][g*N+u] = W_i{g} x_s[b] + b_i{g}   for all steps at once: (N*B x W) . (W x 3N).
+// K = W is tiny (12): the product is bound by writing the (N*B x 3N) result (49 MB at cfg2), so each thread keeps
+// one row of W_ih in registers and streams over a tile of 64 x-rows held in shared memory (coalesced stores).
+template <int WMAX>
+__global__ void __launch_bounds__(256) gru_input_proj_kernel(const float* __restrict__ xs, const float* __restrict__ w_ih,
+                                                             const float* __restrict__ b_ih, float* __restrict__ gi,
+                                                             int SB, int N3, int W) {
+  __shared__ float xt[64][WMAX];
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * 64;
+  const int nr = min(64, SB - r0);
+  for (int i = threadIdx.x; i < 64 * WMAX; i += 256) {      // padded taps must be finite zeros
+    const int r = i / WMAX, t = i % WMAX;
+    xt[r][t] = (r < nr && t < W) ? xs[(long long)(r0 + r) * W + t] : 0.f;
+  }
+  float wr[WMAX];
+  float bias = 0.f;
+  if (row < N3) {
+    bias = __ldg(b_ih + row);
+#pragma unroll
+    for (int t = 0; t < WMAX; ++t) wr[t] = t < W ? __ldg(w_ih + (long long)row * W + t) : 0.f;
+  }
+  __syncthreads();
+  if (row >= N3) return;
+  for (int r = 0; r < nr; ++r) {
+    float acc = bias;
+#pragma unroll
+    for (int t = 0; t < WMAX; ++t) acc = fmaf(wr[t], xt[r][t], acc);     // padded taps multiply zeros
+    gi[(long long)(r0 + r) * N3 + row] = acc;
+  }
+}
+
 int gru_input_proj(const GruArgs& a, cudaStream_t st) {
-  GemmOperands g = {a.xs, a.W, 0, a.w_ih, a.W, 0, nullptr, a.N * a.B, 3 * a.N, a.W};
-  EpiBias<0> epi = {a.gi, 3 * a.N, 0, a.b_ih, 0};
+  const int SB = a.N * a.B, N3 = 3 * a.N;
+  if (a.W <= 16) {
+    dim3 grid(ceil_div(N3, 256), ceil_div(SB, 64));
+    gru_input_proj_kernel<16><<<grid, 256, 0, st>>>(a.xs, a.w_ih, a.b_ih, a.gi, SB, N3, a.W);
+    SG_LAUNCH_CHECK("gru_input_proj_kernel");
+    return 0;
+  }
+  GemmOperands g = {a.xs, a.W, 0, a.w_ih, a.W, 0, nullptr, SB, N3, a.W};
+  EpiBias<0> epi = {a.gi, N3, 0, a.b_ih, 0};
   return launch_sgemm<false, true, false>(g, epi, 1, st, "gru_input_proj");
 }
 

@@ -118,37 +118,54 @@ int launch_gft(const float* mul_L, const float* x_bwn, float* G, float* skbuf, i
 //   forecast        = forecast_source @ Wfr^T + b_fr               :69
 //   backcast        = sigmoid(pre_b + b_b - (x @ Wsc^T + b_sc))    :70-72 (block 0 only)
 
+// one warp per row: the T sigmoids are computed once (not once per output), staged in shared memory, then lanes
+// o < W take the dot products against forecast_result.weight (transposed in shared memory: conflict-free)
 __global__ void __launch_bounds__(256) block_head_kernel(HeadArgs a) {
-  const long long total = (long long)a.R * a.W;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(idx / a.W), o = (int)(idx % a.W);
+  extern __shared__ float sm[];
+  const int T = a.T, W = a.W;
+  float* s_wfr = sm;                    // [T][W]   forecast_result.weight^T
+  float* s_wsc = s_wfr + T * W;         // [W][W]   backcast_short_cut.weight^T
+  float* s_fs = s_wsc + W * W;          // [8][T]
+  float* s_x = s_fs + 8 * T;            // [8][W]
+  for (int i = threadIdx.x; i < T * W; i += blockDim.x) s_wfr[(i % T) * W + i / T] = a.wfr[i];
+  if (a.backcast_bnw != nullptr)
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x) s_wsc[(i % W) * W + i / W] = a.wsc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* fs = s_fs + w * T;
+  float* xr = s_x + w * W;
+  for (int row = blockIdx.x * 8 + w; row < a.R; row += gridDim.x * 8) {
     const float* p = a.pre + (long long)row * a.ldp;
-    const float* w = a.wfr + (long long)o * a.T;
-    float acc = a.bfr[o];
-    for (int u = 0; u < a.T; ++u) {
-      const float fs = sigmoidf_(p[u] + a.bf[u]);
-      acc = fmaf(fs, w[u], acc);
-      if (a.save_fs != nullptr && (u % a.W) == o) a.save_fs[(long long)row * a.T + u] = fs;
+    for (int u = lane; u < T; u += 32) {
+      const float f = sigmoidf_(p[u] + a.bf[u]);
+      fs[u] = f;
+      if (a.save_fs != nullptr) a.save_fs[(long long)row * T + u] = f;
     }
-    a.forecast[idx] = acc;
-    if (a.backcast_bnw != nullptr) {
-      float sc = a.bsc[o];
-      const float* xr = a.x_bnw + (long long)row * a.W;
-      const float* ws = a.wsc + (long long)o * a.W;
-      for (int t = 0; t < a.W; ++t) sc = fmaf(xr[t], ws[t], sc);
-      const float bc = sigmoidf_(p[a.T + o] + a.bb[o] - sc);
-      a.backcast_bnw[idx] = bc;
-      const int b = row / a.N, n = row - b * a.N;
-      a.backcast_bwn[((long long)b * a.W + o) * a.N + n] = bc;
+    if (a.backcast_bnw != nullptr)
+      for (int t = lane; t < W; t += 32) xr[t] = a.x_bnw[(long long)row * W + t];
+    __syncwarp();
+    for (int o = lane; o < W; o += 32) {
+      float acc = a.bfr[o];
+      for (int u = 0; u < T; ++u) acc = fmaf(fs[u], s_wfr[u * W + o], acc);
+      a.forecast[(long long)row * W + o] = acc;
+      if (a.backcast_bnw != nullptr) {
+        float sc = a.bsc[o];
+        for (int t = 0; t < W; ++t) sc = fmaf(xr[t], s_wsc[t * W + o], sc);
+        const float bc = sigmoidf_(p[T + o] + a.bb[o] - sc);
+        a.backcast_bnw[(long long)row * W + o] = bc;
+        const int b = row / a.N, n = row - b * a.N;
+        a.backcast_bwn[((long long)b * W + o) * a.N + n] = bc;
+      }
     }
+    __syncwarp();
   }
 }
 
 int launch_block_head(const HeadArgs& a, cudaStream_t st) {
-  const long long total = (long long)a.R * a.W;
-  const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-  block_head_kernel<<<blocks, 256, 0, st>>>(a);
+  const int blocks = a.R / 8 + 1 < 148 * 8 ? a.R / 8 + 1 : 148 * 8;
+  const size_t smem = (size_t)(a.T * a.W + a.W * a.W + 8 * a.T + 8 * a.W) * sizeof(float);
+  SG_CHECK(smem <= 48 * 1024, "block head: T=%d W=%d need %zu bytes of shared memory", a.T, a.W, smem);
+  block_head_kernel<<<blocks, 256, smem, st>>>(a);
   SG_LAUNCH_CHECK("block_head_kernel");
   return 0;
 }
