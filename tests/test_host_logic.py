@@ -233,3 +233,20 @@ def test_state_checkpoint_roundtrip_and_resume(tmp_path):
     with pytest.raises(RuntimeError):
         torch.save({"format": "other"}, str(tmp_path / "bad.pt"))
         ck.load_checkpoint(str(tmp_path / "bad.pt"))
+
+
+@needs_ref
+def test_unmodified_reference_main_runs_on_top_of_this_repo(tmp_path):
+    """`run_main.py` executes the reference's own main.py against this repo's drop-in packages: argument
+    parsing, CSV load, split, dataset construction, Model construction and norm_stat.json all happen; with
+    `--device cpu` the first forward then fails loudly (there is no CPU fallback).  The GPU half of the same
+    flow (train / validate / test through models.handler) is covered by tests/test_handler_gpu.py."""
+    import subprocess
+    import sys
+    env = dict(os.environ, STEMGNN_WORKDIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "run_main.py"), "--epoch", "1", "--device", "cpu"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode != 0
+    assert "Training configs" in r.stdout and "Total Trainable Params: 1123303" in r.stdout
+    assert "no CPU fallback" in r.stderr
+    assert (tmp_path / "output" / "ECG_data" / "train" / "norm_stat.json").exists()
