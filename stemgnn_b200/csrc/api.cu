@@ -163,6 +163,21 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
     const float* w1r = b.w1f + (size_t)(c * 2 + 1) * d * ncol;
     float* a1 = b.act1 + (size_t)c * R * d;
     float* a2 = b.act2 + (size_t)c * R * d;
+    if (gemm_mode != 1) {   // fused three-layer chain on the tensor cores (activations stay in shared memory)
+      const float* const w[3][2] = {{w1l, w1r},
+                                    {bp.glu_left_w[2 + c], bp.glu_right_w[2 + c]},
+                                    {bp.glu_left_w[4 + c], bp.glu_right_w[4 + c]}};
+      const float* const bias[3][2] = {{bp.glu_left_b[c], bp.glu_right_b[c]},
+                                       {bp.glu_left_b[2 + c], bp.glu_right_b[2 + c]},
+                                       {bp.glu_left_b[4 + c], bp.glu_right_b[4 + c]}};
+      const bool keep = b.save_l[c] != nullptr;         // training: the backward needs every layer's tensors
+      float* const act[2] = {keep ? a1 : nullptr, keep ? a2 : nullptr};
+      float* const sl[3] = {b.save_l[c], b.save_l[2 + c], b.save_l[4 + c]};
+      float* const ss[3] = {b.save_s[c], b.save_s[2 + c], b.save_s[4 + c]};
+      const int rc = glu_chain_tc(R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss, st);
+      if (rc == 0) continue;
+      if (rc > 0) return rc;
+    }
     SG_TRY(glu_layer(R, d, ncol, b.G, ncol, w1l, bp.glu_left_b[c], w1r, bp.glu_right_b[c], a1, d,
                      b.save_l[c], b.save_s[c], gemm_mode, st));
     SG_TRY(glu_layer(R, d, d, a1, d, bp.glu_left_w[2 + c], bp.glu_left_b[2 + c], bp.glu_right_w[2 + c],

@@ -288,6 +288,188 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   }
 }
 
+// ---- fused 3-layer GLU chain ------------------------------------------------------------------------------
+// One CTA carries its 128 rows through GLU layer 1 -> 2 -> 3 of one chain (real or imag, base_model.py:52-54):
+// the gated output of a layer is written by the epilogue straight into shared memory in the 128B-swizzled
+// K-major layout the next layer's tcgen05.mma reads as its A operand, so activations never round-trip through
+// L2/HBM between layers (they are only written out when the backward needs them) and 3 launches become 1.
+// Weights stream through a 3-stage ring of 64-byte-row tiles (16 fp32 along K per stage).
+struct GluChainArgs {
+  const float* bl[3]; const float* br[3];
+  float* out3; int ldo3;                 // layer-3 output (act3 column block)
+  float* act[2];                         // layer-1 / layer-2 outputs (R, N) or null (eval)
+  float* save_l[3]; float* save_s[3];    // (R, N) each or null
+  int M, N, K1;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+glu_chain_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_w1l,
+                    const __grid_constant__ CUtensorMap map_w1r, const __grid_constant__ CUtensorMap map_w2l,
+                    const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w3l,
+                    const __grid_constant__ CUtensorMap map_w3r, GluChainArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NSTG = 3;
+  constexpr uint32_t A_CHUNK = TC_BM * 128;            // 128 rows x 32 fp32
+  const int N = g.N;
+  const uint32_t w_bytes = (uint32_t)N * 64;            // N rows x 16 fp32
+  const uint32_t stage_bytes = 2 * w_bytes;
+  uint8_t* a_buf = smem;                                // 8 chunks
+  uint8_t* w_buf = smem + 8 * A_CHUNK;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(w_buf + NSTG * stage_bytes);
+  uint64_t* empty_bar = full_bar + NSTG;
+  uint64_t* tmem_full_bar = empty_bar + NSTG;
+  uint64_t* a_ready_bar = tmem_full_bar + 1;            // epilogue -> MMA: next A tile written, TMEM drained
+  uint64_t* g_full_bar = a_ready_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);   // [3][2][N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const CUtensorMap* wmaps[3][2] = {{&map_w1l, &map_w1r}, {&map_w2l, &map_w2r}, {&map_w3l, &map_w3r}};
+  int nkb[3];
+  nkb[0] = (g.K1 + 15) / 16;
+  nkb[1] = nkb[2] = (N + 15) / 16;
+  const int g_chunks = (g.K1 + 31) / 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(a_ready_bar, 128);
+    mbar_init(g_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer: the input tile once, then the weights of the three layers =====
+      mbar_arrive_expect_tx(g_full_bar, (uint32_t)g_chunks * A_CHUNK);
+      for (int c = 0; c < g_chunks; ++c) tma_load_2d(a_buf + (size_t)c * A_CHUNK, &map_g, g_full_bar, c * 32, m0);
+      int it = 0;
+      for (int l = 0; l < 3; ++l) {
+        for (int kb = 0; kb < nkb[l]; ++kb, ++it) {
+          const int s = it % NSTG;
+          const uint32_t ph = (uint32_t)(it / NSTG) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = w_buf + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_2d(st, wmaps[l][0], &full_bar[s], kb * 16, 0);
+          tma_load_2d(st + w_bytes, wmaps[l][1], &full_bar[s], kb * 16, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_tf32(N);
+      const uint32_t a_addr = smem_u32(a_buf);
+      mbar_wait(g_full_bar, 0);
+      int it = 0;
+      for (int l = 0; l < 3; ++l) {
+        if (l > 0) {                       // A tile of this layer written by the epilogue, TMEM free again
+          mbar_wait(a_ready_bar, (uint32_t)(l - 1) & 1u);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < nkb[l]; ++kb, ++it) {
+          const int s = it % NSTG;
+          const uint32_t ph = (uint32_t)(it / NSTG) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t wl_addr = smem_u32(w_buf + (size_t)s * stage_bytes), wr_addr = wl_addr + w_bytes;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k0 = kb * 16 + kk * 8;
+            const uint64_t ad = umma_desc_sw128(a_addr + (uint32_t)(k0 >> 5) * A_CHUNK + (uint32_t)(k0 & 31) * 4);
+            const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+            umma_tf32(tmem_base, ad, umma_desc_sw64(wl_addr + kk * 32), idesc, acc);
+            umma_tf32(tmem_base + TC_RIGHT_COL, ad, umma_desc_sw64(wr_addr + kk * 32), idesc, acc);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(tmem_full_bar);
+      }
+    }
+  } else {             // ===== epilogue: warps 2..5 =====
+    for (int i = threadIdx.x - 64; i < 3 * N; i += 128) {
+      const int l = i / N, c = i - l * N;
+      s_bias[(l * 2 + 0) * N + c] = __ldg(g.bl[l] + c);
+      s_bias[(l * 2 + 1) * N + c] = __ldg(g.br[l] + c);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int quarter = warp & 3;
+    const int rloc = quarter * 32 + lane;               // row inside the tile = TMEM lane
+    const int row = m0 + rloc;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int l = 0; l < 3; ++l) {
+      mbar_wait(tmem_full_bar, (uint32_t)l & 1u);
+      tc_fence_after();
+      const float* sbl = s_bias + (l * 2 + 0) * N;
+      const float* sbr = s_bias + (l * 2 + 1) * N;
+      float* gout = l == 2 ? g.out3 : g.act[l];
+      const int ldo = l == 2 ? g.ldo3 : N;
+      for (int c = 0; c < N; c += 16) {
+        float lv[16], rv[16], o[16];
+        tmem_ld16(taddr + c, lv);
+        tmem_ld16(taddr + TC_RIGHT_COL + c, rv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          lv[j] += sbl[c + j];
+          rv[j] = __fdividef(1.0f, 1.0f + __expf(-(rv[j] + sbr[c + j])));
+          o[j] = lv[j] * rv[j];
+        }
+        if (l < 2) {   // next layer's A operand: K-major rows of 128 bytes, 16-byte chunks XOR-swizzled by row%8
+          uint8_t* chunk = a_buf + (size_t)(c >> 5) * A_CHUNK + (size_t)rloc * 128;
+          const int cc0 = (c & 31) >> 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(chunk + (((cc0 + j) ^ (rloc & 7)) << 4)) =
+                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        if (row < g.M) {
+          if (gout != nullptr) {
+            float4* po = reinterpret_cast<float4*>(gout + (size_t)row * ldo + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) po[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          if (g.save_l[l] != nullptr) {
+            float4* pl = reinterpret_cast<float4*>(g.save_l[l] + (size_t)row * N + c);
+            float4* ps = reinterpret_cast<float4*>(g.save_s[l] + (size_t)row * N + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pl[j] = make_float4(lv[4 * j], lv[4 * j + 1], lv[4 * j + 2], lv[4 * j + 3]);
+              ps[j] = make_float4(rv[4 * j], rv[4 * j + 1], rv[4 * j + 2], rv[4 * j + 3]);
+            }
+          }
+        }
+      }
+      if (l < 2) {
+        tc_fence_before();                                               // TMEM reads done before the next MMAs
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor core
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready_bar)) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ---- generic TF32 GEMM: C[M,N] (+)= A[M,K] B[N,K]^T, both operands K-major ------------------------------
 // Same pipeline as glu_tc_kernel with one B operand.  gridDim.y splits K (partial sums are added with
 // atomics: gradient buffers accumulate by contract).  Rows m >= msplit go to the second output C1
@@ -524,6 +706,51 @@ int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const flo
   dim3 grid(ceil_div(M, TC_BM), splits);
   tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, g);
   SG_LAUNCH_CHECK("tc_gemm_kernel");
+  return 0;
+}
+
+
+// Fused GLU chain (3 layers of one chain) on tcgen05.  w[l][0/1] = left/right weights of layer l ((N, K_l) row
+// major, K_1 = K1, K_2 = K_3 = N).  act[0..1], save_l/save_s may be null (eval).  Returns -1 when unsupported.
+int glu_chain_tc(int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
+                 const float* const bias[3][2], float* out3, int ldo3, float* const act[2],
+                 float* const save_l[3], float* const save_s[3], cudaStream_t st) {
+  static const bool off = getenv("STEMGNN_GLU_UNFUSED") != nullptr;
+  if (off) return -1;
+  if (N % 16 != 0 || N < 16 || N > 256 || K1 < 1 || K1 > 256 || (K1 & 3) != 0 || (ldg & 3) != 0 || (ldo3 & 3) != 0)
+    return -1;
+  if ((reinterpret_cast<uintptr_t>(G) & 15) || (reinterpret_cast<uintptr_t>(out3) & 15)) return -1;
+  for (int l = 0; l < 3; ++l)
+    for (int sd = 0; sd < 2; ++sd)
+      if (reinterpret_cast<uintptr_t>(w[l][sd]) & 15) return -1;
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -1;
+  CUtensorMap mg, mw[3][2];
+  if (!make_map(enc, &mg, G, M, K1, ldg, TC_BM, 32)) return -1;
+  for (int l = 0; l < 3; ++l)
+    for (int sd = 0; sd < 2; ++sd) {
+      const int K = l == 0 ? K1 : N;
+      if (!make_map(enc, &mw[l][sd], w[l][sd], N, K, K, N, 16)) return -1;
+    }
+  const size_t smem = (size_t)8 * TC_BM * 128 + (size_t)3 * 2 * N * 64 + 128 + (size_t)6 * N * sizeof(float) + 1024;
+  if (smem > 227 * 1024) return -1;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    SG_CUDA(cudaFuncSetAttribute(glu_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  GluChainArgs g = {};
+  for (int l = 0; l < 3; ++l) {
+    g.bl[l] = bias[l][0];
+    g.br[l] = bias[l][1];
+    g.save_l[l] = save_l[l];
+    g.save_s[l] = save_s[l];
+  }
+  g.out3 = out3; g.ldo3 = ldo3; g.act[0] = act[0]; g.act[1] = act[1];
+  g.M = M; g.N = N; g.K1 = K1;
+  glu_chain_tc_kernel<<<ceil_div(M, TC_BM), TC_THREADS, smem, st>>>(mg, mw[0][0], mw[0][1], mw[1][0], mw[1][1],
+                                                                     mw[2][0], mw[2][1], g);
+  SG_LAUNCH_CHECK("glu_chain_tc_kernel");
   return 0;
 }
 

@@ -78,6 +78,11 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
                 const float* Wr, const float* br, float* out, int ldo, float* save_l, float* save_s,
                 int lds, cudaStream_t st);
 
+// fused 3-layer GLU chain on tcgen05 (glu_tc.cu); -1 = unsupported shape (use the per-layer kernels)
+int glu_chain_tc(int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
+                 const float* const bias[3][2], float* out3, int ldo3, float* const act[2],
+                 float* const save_l[3], float* const save_s[3], cudaStream_t st);
+
 // generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
             float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st);
