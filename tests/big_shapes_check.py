@@ -1,4 +1,4 @@
-"""Scratch: large-shape sanity (cfg4 global batch, cfg5 N=2048 shard) — forward + backward finite and
+"""Manual check (not collected by pytest; run on the GPU box): large-shape sanity (cfg4 global batch, cfg5 N=2048 shard) — forward + backward finite and
 consistent with the host port where the port is affordable."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -2,7 +2,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import torch_port as tp
+from stemgnn_b200 import synthetic as tp
 from models.base_model import Model
 
 B, N, W, H = [int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (32, 358, 12, 3))]
