@@ -324,6 +324,9 @@ def run_ours(args, rank, world, local_rank):
                 # projection it streams + 1.5 MB of W_hh per cluster wave
                 "traffic": 50.83e6, "traffic_unit": "bytes/launch", "peak_source": peak_src,
                 "ms_per_launch": gru_ms, "share_of_step": gru_ms / (dev_ms / args.steps),
+                # context: this is an fp32 FFMA2 kernel (no tensor-core form keeps fp32 parity and fits the DSMEM
+                # exchange budget); against the fp32 FMA peak of 148 SMs x 128 FMA/clk x 1.965 GHz:
+                "fp32_fma_peak_tflops": 74.4, "frac_of_fp32_fma_peak": ach / 74.4,
                 "note": "latency-bound recurrence: 358 dependent steps; flops = 6BN^3 + 12BN^2"}
     cpu_steps = 15
     cpu_v, cpu_ms, threads = cpu_reference_forward(cpu_steps, 2)
