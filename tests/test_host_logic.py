@@ -250,3 +250,41 @@ def test_unmodified_reference_main_runs_on_top_of_this_repo(tmp_path):
     assert "Training configs" in r.stdout and "Total Trainable Params: 1123303" in r.stdout
     assert "no CPU fallback" in r.stderr
     assert (tmp_path / "output" / "ECG_data" / "train" / "norm_stat.json").exists()
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_layout(tmp_path):
+    """include/stemgnn_b200.h compiles as C (gcc -std=c99) and its struct layout equals the ctypes mirror that
+    the Python host side passes through the ABI."""
+    import ctypes
+    import shutil
+    import subprocess
+    from stemgnn_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "stemgnn_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(stemgnn_dims_t), sizeof(stemgnn_block_params_t), sizeof(stemgnn_params_t),
+         sizeof(stemgnn_fwd_opts_t), sizeof(stemgnn_grads_t));
+  printf("%zu %zu %zu %zu\\n", offsetof(stemgnn_params_t, block), offsetof(stemgnn_params_t, fc0_w),
+         offsetof(stemgnn_block_params_t, glu_left_w), offsetof(stemgnn_block_params_t, glu_right_b));
+  printf("%zu %zu %zu %zu\\n", offsetof(stemgnn_fwd_opts_t, dropout_seed), offsetof(stemgnn_fwd_opts_t, dropout_mask),
+         offsetof(stemgnn_fwd_opts_t, gemm_mode), offsetof(stemgnn_fwd_opts_t, reuse_folded));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(v) for v in out]
+    assert sizes[:5] == [ctypes.sizeof(_lib.Dims), ctypes.sizeof(_lib.BlockPtrs), ctypes.sizeof(_lib.ModelPtrs),
+                         ctypes.sizeof(_lib.FwdOpts), ctypes.sizeof(_lib.ModelPtrs)]
+    assert sizes[5:9] == [_lib.ModelPtrs.block.offset, _lib.ModelPtrs.fc0_w.offset,
+                          _lib.BlockPtrs.glu_left_w.offset, _lib.BlockPtrs.glu_right_b.offset]
+    assert sizes[9:13] == [_lib.FwdOpts.dropout_seed.offset, _lib.FwdOpts.dropout_mask.offset,
+                           _lib.FwdOpts.gemm_mode.offset, _lib.FwdOpts.reuse_folded.offset]
