@@ -2,19 +2,22 @@
 """bench.py — forecast-windows/sec of the StemGNN hot path on B200 (BASELINE.json metric).
 
 A "step" is ONE pass of the hot path (Model.forward in eval(), no_grad — SURVEY.md §8(d)) over one
-batch of synthetic windows at the north-star shape (B,N,W,H)=(32,358,12,3) per GPU (weak scaling:
-every rank owns its own batch; the eval path has no collective).
+batch of windows per GPU (weak scaling: every rank owns its own batch; the eval path has no collective).
+Default workload = BASELINE.json configs[1], the shape the metric is quoted on: (B,N,W,H)=(32,358,12,3).
 
-    python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [...]                      # the reference's CPU path (oracle port)
+    python bench.py [--gpus N --steps K --warmup W] [--config cfg1..cfg5]     # this repo's CUDA path
+    python bench.py --impl reference [...]                                    # the reference's own CPU path
 
 Prints ONE JSON line.  Keys (see the task contract):
   value / ms_per_step   device-timed (CUDA events, L2 flushed between steps), inputs resident in HBM
   e2e                   same metric through the public API with HOST buffers: pinned x -> H2D ->
                         Model.forward -> D2H of the forecast, all inside the timed region
+  parity                "MAE vs ref" half of the metric: utils.math_utils.MAE and allclose(rtol 1e-3, atol 1e-4)
+                        between this forward and the reference's CPU forward on the SAME inputs/weights
   roofline              the dominant kernel (GRU recurrence), timed live with CUDA events via the
                         library's stemgnn_profile_gru hook; flops = SURVEY.md §8(d) GRU terms
-  cpu_baseline          oracle/torch_port.py (the reference's ATen op sequence) on the host cores
+  cpu_baseline          the unmodified reference (baseline/_ref or /root/reference under oracle/ref_shim.py;
+                        kind "reference") — or the torch port when no copy is present (kind "port") — on the host cores
 """
 import argparse
 import ctypes
@@ -27,19 +30,44 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B, N, W, H, MULTI = 32, 358, 12, 3, 5
-WORKLOAD = "synthetic N=358 W=12 H=3 batch=32 fp32 eval forward (BASELINE.json configs[1])"
+MULTI = 5
 METRIC = "forecast-windows/sec (B,N,W)=(32,358,12)"
-FORWARD_FLOPS = 28140101688      # SURVEY.md §8(d) dead-work-free count at (32,358,12,3); = oracle.forward_flops
+# BASELINE.json configs; B is per GPU (cfg4: global 128 on 4 GPUs, cfg5: global 256 on 8 GPUs)
+CONFIGS = {
+    "cfg1": dict(B=32, N=140, W=12, H=3, gemm="auto",
+                 workload="ECG_data.csv N=140 W=12 H=3 batch=32 fp32 eval forward (BASELINE.json configs[0])"),
+    "cfg2": dict(B=32, N=358, W=12, H=3, gemm="auto",
+                 workload="synthetic N=358 W=12 H=3 batch=32 fp32 eval forward (BASELINE.json configs[1])"),
+    "cfg3": dict(B=64, N=228, W=12, H=3, gemm="bf16",
+                 workload="PeMS07 shape N=228 W=12 H=3 batch=64 bf16 tensor-core GFT eval forward (BASELINE.json configs[2])"),
+    "cfg4": dict(B=32, N=325, W=12, H=12, gemm="auto",
+                 workload="synthetic N=325 W=12 H=12 batch=32 per GPU (global 128 on 4 GPUs) eval forward (BASELINE.json configs[3])"),
+    "cfg5": dict(B=32, N=2048, W=12, H=3, gemm="auto",
+                 workload="synthetic N=2048 W=12 H=3 batch=32 per GPU (global 256 on 8 GPUs) eval forward (BASELINE.json configs[4])"),
+}
+
+
+def config_dict(name, world):
+    """The `config` object of the JSON line — identical for both arms (ours / --impl reference)."""
+    c = CONFIGS[name]
+    return {"workload": c["workload"], "name": name, "B_per_gpu": c["B"], "N": c["N"], "W": c["W"], "H": c["H"],
+            "multi_layer": MULTI, "mode": "eval forward (Model.forward, no_grad)",
+            "parallelism": f"dp{world} replicas"}
 
 
 def _peaks():
+    extra = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_measured_peaks_tf32_fp32.json")) as f:
+            extra = json.load(f)
+    except Exception:
+        pass
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
+        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)", extra
     except Exception:
-        return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return 1590.0, 6650.0, "fallback (B200_PROFILING.md)", extra
 
 
 class ClockSampler:
@@ -99,75 +127,91 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
 
 
-def cpu_reference_forward(steps, warmup):
-    """The reference's CPU path: oracle/torch_port.model_forward (same ATen ops as base_model.py) on the
-    host cores.  torchrun pins OMP_NUM_THREADS=1 and "all cores" is not the fastest setting on a
-    128-thread host, so the thread count is picked as the best of a short sweep (the reference gets its
-    best shot).  Returns (windows_per_s, ms_per_step, threads)."""
+def make_inputs(name, rank):
+    """(x (B,W,N), y (B,H,N), data tag).  cfg1 uses z-scored rows of the reference's ECG_data.csv when the staged
+    copy (baseline/_ref/dataset, shipped by oracle/fetch_reference.py) is present; everything else — and cfg1
+    without the CSV — uses the seeded synthetic generator of SURVEY.md §8(d)."""
+    import numpy as np
     import torch
-    from oracle import torch_port as tp
-    p = tp.synthetic_params(N, W, H, MULTI, seed=0)
-    x, _ = tp.synthetic_batch(B, N, W, H)
-    ncpu = os.cpu_count() or 8
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu // 2, ncpu) if 1 <= c <= ncpu})
-    best, best_t = None, None
-    with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            tp.model_forward(x, p)
-            t0 = time.perf_counter()
-            tp.model_forward(x, p)
-            dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best, best_t = c, dt
-        torch.set_num_threads(best)
-        for _ in range(warmup):
-            tp.model_forward(x, p)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            tp.model_forward(x, p)
-        dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3, best
+    from stemgnn_b200 import synthetic
+    c = CONFIGS[name]
+    if name == "cfg1":
+        for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+            csv = os.path.join(root, "dataset", "ECG_data.csv")
+            if os.path.isfile(csv):
+                data = np.loadtxt(csv, delimiter=",", dtype=np.float64)
+                data = (data - data.mean(axis=0)) / (data.std(axis=0) + 1e-12)       # z_score over the file
+                hi = [c["W"] + 97 * i + 13 * rank for i in range(c["B"])]            # B spread-out windows
+                x = np.stack([data[h - c["W"]:h] for h in hi]).astype(np.float32)
+                y = np.stack([data[h:h + c["H"]] for h in hi]).astype(np.float32)
+                return torch.from_numpy(x), torch.from_numpy(y), "ECG_data.csv rows (z-scored), reference dataset"
+    x, y = synthetic.synthetic_batch(c["B"], c["N"], c["W"], c["H"], seed=1234 + rank)
+    return x, y, "synthetic"
+
+
+def cpu_reference(name, budget_s=20.0, max_steps=15):
+    """Times the reference's CPU forward on this host for `name`: (CpuReference, x, ms/forward, steps, threads)."""
+    import torch
+    from oracle.cpu_reference import CpuReference
+    from stemgnn_b200 import synthetic
+    c = CONFIGS[name]
+    p = synthetic.synthetic_params(c["N"], c["W"], c["H"], MULTI, seed=0)
+    ref = CpuReference(c["N"], c["W"], c["H"], MULTI, p)
+    x, _y, _tag = make_inputs(name, 0)
+    threads = ref.pick_threads(x, cands=None if c["N"] <= 512 else [min(32, os.cpu_count() or 8), os.cpu_count() or 8])
+    t0 = time.perf_counter()
+    ref.forward(x)
+    one = time.perf_counter() - t0
+    steps = max(1, min(max_steps, int(budget_s / max(one, 1e-3))))
+    ms = ref.time_forward(x, steps, 1 if one < 2.0 else 0) * 1e3
+    return ref, x, ms, steps, threads
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 40))
-    v, ms, threads = cpu_reference_forward(steps, max(1, min(args.warmup, 3)))
+    c = CONFIGS[args.config]
+    ref, _x, ms, steps, threads = cpu_reference(args.config, budget_s=30.0, max_steps=max(1, min(args.steps, 40)))
+    v = c["B"] / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "windows/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "B": B, "N": N, "W": W, "H": H,
-                       "note": "reference CPU path = oracle/torch_port.py (reference's ATen op sequence; "
-                               "the Python reference itself cannot travel to the GPU box)"},
-            "cpu_baseline": {"value": v, "unit": "windows/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} eval forwards of one {B}-window batch; os.cpu_count()={os.cpu_count()}"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": make_inputs(args.config, 0)[2],
+            "config": config_dict(args.config, world),
+            "impl_notes": f"reference CPU path = {ref.kind} ({ref.source}), torch {__import__('torch').__version__} CPU, "
+                          f"{threads} threads (best of a sweep)",
+            "cpu_baseline": {"value": v, "unit": "windows/s", "cores": threads, "kind": ref.kind,
+                             "sample": f"{steps} eval forwards of one {c['B']}-window batch; os.cpu_count()={os.cpu_count()}"},
             "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 def run_ours(args, rank, world, local_rank):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from models.base_model import Model
     from stemgnn_b200 import synthetic as tp      # seeded weights / inputs (plain data generators)
-    from stemgnn_b200 import _lib
+    from stemgnn_b200 import _lib, runtime as _rt
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
+    cfg = CONFIGS[args.config]
+    B, N, W, H = cfg["B"], cfg["N"], cfg["W"], cfg["H"]
+    gemm_mode = {"auto": _rt.GEMM_AUTO, "bf16": getattr(_rt, "GEMM_BF16", _rt.GEMM_AUTO)}[cfg["gemm"]]
 
     model = Model(N, 2, W, MULTI, horizon=H)
     model.load_state_dict(tp.synthetic_params(N, W, H, MULTI, seed=0))
     model = model.to(dev).eval()
-    x_host, _ = tp.synthetic_batch(B, N, W, H, seed=1234 + rank)
+    model.gemm_mode = gemm_mode
+    x_host, y_host, data_tag = make_inputs(args.config, rank)
     x_host = x_host.pin_memory()
     x_dev = x_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    steps = args.steps if N <= 512 else max(3, min(args.steps, 10))    # cfg5: seconds per step
 
     def barrier():
         torch.cuda.synchronize()
@@ -180,27 +224,27 @@ def run_ours(args, rank, world, local_rank):
             model(x_dev)
         # ---- device-timed: inputs resident in HBM, L2 flushed between steps -------------------
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-              for _ in range(args.steps)]
+              for _ in range(steps)]
         sampler = ClockSampler(local_rank) if rank == 0 else None
         barrier()
         launches0 = lib.stemgnn_launch_count()
-        for i in range(args.steps):
+        for i in range(steps):
             flush.zero_()
             ev[i][0].record()
-            model(x_dev)
+            f_dev, _a = model(x_dev)
             ev[i][1].record()
         barrier()
         launches = lib.stemgnn_launch_count() - launches0
         clocks = sampler.stop() if sampler else None
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        forecast_ours = f_dev.float().cpu()
 
         # ---- same forward with every GEMM forced to exact fp32 FFMA2 (Model.gemm_mode = 1) ---------------
-        from stemgnn_b200 import runtime as _rt
         model.gemm_mode = _rt.GEMM_FP32
         for _ in range(3):
             model(x_dev)
         ev32 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                for _ in range(min(args.steps, 20))]
+                for _ in range(min(steps, 20))]
         for a0, a1 in ev32:
             flush.zero_()
             a0.record()
@@ -208,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
             a1.record()
         torch.cuda.synchronize()
         fp32_ms = sum(a0.elapsed_time(a1) for a0, a1 in ev32) / len(ev32)
-        model.gemm_mode = _rt.GEMM_AUTO
+        model.gemm_mode = gemm_mode
         model(x_dev)
 
         # ---- dominant kernel (GRU recurrence) with CUDA events on the launching stream --------------
@@ -218,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); e1.record(); torch.cuda.synchronize()           # materialise the handles
             tot = 0.0
-            reps = min(args.steps, 10)
+            reps = min(steps, 10)
             for _ in range(reps):
                 flush.zero_()
                 lib.stemgnn_profile_gru(e0.cuda_event, e1.cuda_event)
@@ -231,32 +275,12 @@ def run_ours(args, rank, world, local_rank):
             gru_ms = None
             sys.stderr.write(f"[bench] GRU event hook failed: {exc}\n")
 
-        # ---- the tcgen05 GLU layer (61 % of the flops), timed alone through the C ABI with CUDA events ----
-        glu_ms = None
+        # ---- the fused tcgen05 GLU chain (61 % of the flops), timed alone through the C ABI ------------------
+        glu_ms, glu_flops = None, None
         try:
-            R, d = B * N, 4 * MULTI * W
-            ga = torch.randn(R, d, device=dev)
-            gw = [torch.randn(d, d, device=dev) / d ** 0.5 for _ in range(2)]
-            gb = [torch.zeros(d, device=dev) for _ in range(2)]
-            go = torch.empty(R, d, device=dev)
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
-            def glu_call():
-                rc = lib.stemgnn_glu_gemm(R, d, d, ga.data_ptr(), d, gw[0].data_ptr(), gb[0].data_ptr(),
-                                          gw[1].data_ptr(), gb[1].data_ptr(), go.data_ptr(), d, 1, st)
-                if rc:
-                    raise RuntimeError(lib.stemgnn_last_error().decode())
-            for _ in range(3):
-                glu_call()
-            tot, reps = 0.0, 10
-            for _ in range(reps):
-                flush.zero_()
-                e0.record(); glu_call(); e1.record()
-                torch.cuda.synchronize()
-                tot += e0.elapsed_time(e1)
-            glu_ms = tot / reps
+            glu_ms, glu_flops = time_glu_chain(lib, dev, B, N, W, flush)
         except Exception as exc:
-            sys.stderr.write(f"[bench] GLU kernel timing failed: {exc}\n")
+            sys.stderr.write(f"[bench] GLU chain timing failed: {exc}\n")
 
         # ---- end to end through the public API with host buffers ----------------------------------
         out_host = torch.empty(B, H, N).pin_memory()
@@ -265,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
             out_host.copy_(f, non_blocking=True)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             xd = x_host.to(dev, non_blocking=True)                      # H2D of the step's input
             f, _a = model(xd)
             out_host.copy_(f, non_blocking=True)                        # D2H of the step's result
@@ -273,37 +297,15 @@ def run_ours(args, rank, world, local_rank):
         e2e_s = time.perf_counter() - t0
         barrier()
 
-    # ---- second column: training step (handler.py:160-165) = zero_grad + forward (train mode, Philox
-    #      dropout) + MSE + backward (+ the single flat-gradient all-reduce at N>1) + RMSprop ----------
-    from stemgnn_b200 import ddp
-    ddp.attach(model)
-    model.train()
-    y_dev = tp.synthetic_batch(B, N, W, H, seed=1234 + rank)[1].to(dev)
-    optim = torch.optim.RMSprop(model.parameters(), lr=1e-4, eps=1e-8)
-    crit = torch.nn.MSELoss()
-
-    def train_step():
-        model.zero_grad()
-        f, _a = model(x_dev)
-        loss = crit(f, y_dev)
-        loss.backward()
-        optim.step()
-        return loss
-
-    t_steps = max(5, min(args.steps, 20))
-    for _ in range(3):
-        train_step()
-    tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(t_steps)]
-    barrier()
-    for i in range(t_steps):
-        flush.zero_()
-        tev[i][0].record()
-        train_step()
-        tev[i][1].record()
-    barrier()
-    train_ms = sum(a.elapsed_time(b) for a, b in tev)
+    # ---- second column: training step (handler.py:160-165) ----------------------------------------------
+    train = None
+    try:
+        train = time_train_step(model, x_dev, y_host.to(dev), flush, barrier, steps, world)
+    except Exception as exc:
+        sys.stderr.write(f"[bench] train-step timing failed: {exc}\n")
     model.eval()
 
+    train_ms = train["total_ms"] if train else 0.0
     t = torch.tensor([dev_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,58 +313,150 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
 
-    peak_tf, peak_gbs, peak_src = _peaks()
+    peak_tf, peak_gbs, peak_src, extra_peaks = _peaks()
     gru_flops = 6.0 * B * N ** 3 + 12.0 * B * N * N               # recurrence + gates
     roof = None
     if gru_ms:
         ach = gru_flops / (gru_ms * 1e-3) / 1e12
-        roof = {"kernel": "gru_cluster_kernel (GRU recurrence, fp32 FFMA2, 16-CTA clusters)",
-                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                # (profiles/r01_ncu_gru_cluster_v3_raw.csv): 50.79 MB + 0.04 MB; algorithmic: the 49.2 MB input
-                # projection it streams + 1.5 MB of W_hh per cluster wave
-                "traffic": 50.83e6, "traffic_unit": "bytes/launch", "peak_source": peak_src,
-                "ms_per_launch": gru_ms, "share_of_step": gru_ms / (dev_ms / args.steps),
-                # context: this is an fp32 FFMA2 kernel (no tensor-core form keeps fp32 parity and fits the DSMEM
-                # exchange budget); against the fp32 FMA peak of 148 SMs x 128 FMA/clk x 1.965 GHz:
-                "fp32_fma_peak_tflops": 74.4, "frac_of_fp32_fma_peak": ach / 74.4,
-                "note": "latency-bound recurrence: 358 dependent steps; flops = 6BN^3 + 12BN^2"}
-    cpu_steps = 15
-    cpu_v, cpu_ms, threads = cpu_reference_forward(cpu_steps, 2)
-    value = world * B * args.steps / (dev_ms * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (GLU chain + folded output map: tf32 tensor-core operands, fp32 accumulate; see exact_fp32)",
-            "data": "synthetic",
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_gru_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("config") == args.config:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"kernel": lib.stemgnn_gru_kernel_name().decode() if hasattr(lib, "stemgnn_gru_kernel_name") else "gru",
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write of profiles/r02_gru_traffic.json)"
+                if traffic else None,
+                "peak_source": peak_src, "ms_per_launch": gru_ms, "share_of_step": gru_ms / (dev_ms / steps),
+                "algorithmic_flops_per_launch": gru_flops, "measured_other_peaks": extra_peaks,
+                "note": f"recurrence of {N} dependent steps; flops = 6BN^3 + 12BN^2 (SURVEY.md §8(d))"}
+
+    # ---- parity: "MAE vs ref" on the SAME inputs / weights, reference CPU forward timed beside it ----------------
+    ref, x_ref, cpu_ms, cpu_steps, threads = cpu_reference(args.config)
+    f_ref, _a_ref = ref.forward(x_ref)
+    err = (forecast_ours.double() - f_ref.double()).abs()
+    parity = {"mae_vs_ref": float(err.mean()), "max_abs_err": float(err.max()),
+              "allclose_rtol1e-3_atol1e-4": bool((err <= 1e-4 + 1e-3 * f_ref.double().abs()).all()),
+              "ref": ref.kind, "ref_source": ref.source,
+              "what": "utils.math_utils.MAE / allclose between this run's timed forecast (rank 0) and the reference CPU forward"}
+    cpu_v = B / (cpu_ms * 1e-3)
+    value = world * B * steps / (dev_ms * 1e-3)
+    prec = {"auto": "f32 (GLU chain / GFT / output map on tcgen05 with split operands, fp32 accumulate; see exact_fp32)",
+            "bf16": "bf16 tensor-core operands (GLU chain, GFT), fp32 accumulate"}[cfg["gemm"]]
+    line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": data_tag,
             "exact_fp32": {"value": B / (fp32_ms * 1e-3) * world, "unit": "windows/s", "ms_per_step": fp32_ms,
                            "what": "same forward with every GEMM on the fp32 FFMA2 path (Model.gemm_mode = 1), rank 0"},
-            "config": {"workload": WORKLOAD, "B_per_gpu": B, "N": N, "W": W, "H": H, "multi_layer": MULTI,
-                       "mode": "eval forward (Model.forward, no_grad)", "parallelism": f"dp{world} replicas",
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-                       "flops_per_step": FORWARD_FLOPS},
-            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
+            "config": config_dict(args.config, world),
+            "impl_notes": {"l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+                           "reuse_folded": "eval forwards reuse the DFT-folded / pre-split weights while no parameter "
+                                           "changed (weight pre-packing, stemgnn_fwd_opts_t.reuse_folded)",
+                           "flops_per_step": forward_flops(B, N, W, H)},
+            "parity": parity,
+            "e2e": {"value": world * B * steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": B * W * N * 4, "d2h_bytes_per_step": B * H * N * 4,
-                    "ms_per_step": e2e_ms / args.steps},
-            "train": {"value": world * B * t_steps / (train_ms * 1e-3), "unit": "windows/s",
-                      "ms_per_step": train_ms / t_steps, "steps": t_steps,
-                      "what": "zero_grad + forward(train, Philox dropout) + MSE + backward"
-                              + (" + flat-gradient NCCL all-reduce" if world > 1 else "") + " + RMSprop step"},
+                    "ms_per_step": e2e_ms / steps},
+            "train": None if not train else {
+                "value": world * B * train["steps"] / (train_ms * 1e-3), "unit": "windows/s",
+                "ms_per_step": train_ms / train["steps"], "steps": train["steps"], "what": train["what"]},
             "gpu_launches": int(launches),
             "roofline": roof,
             "roofline_glu": None if not glu_ms else {
-                "kernel": "glu_tc_kernel (tcgen05 kind::tf32, one 240->240 GLU layer over B*N=11456 rows)",
-                "bound": "tensor", "achieved": 4.0 * B * N * 240 * 240 / (glu_ms * 1e-3) / 1e12,
-                "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": 4.0 * B * N * 240 * 240 / (glu_ms * 1e-3) / 1e12 / peak_tf,
-                "ms_per_launch": glu_ms, "peak_source": peak_src + " (bf16 figure; TF32 runs at half rate)",
-                "note": "L2 flushed before each launch: weights and activations come from HBM"},
-            "cpu_baseline": {"value": cpu_v, "unit": "windows/s", "cores": threads, "kind": "port",
+                "kernel": "glu_chain_tc_kernel (tcgen05, the 3 GLU layers of one chain over B*N rows, one launch)",
+                "bound": "tensor", "achieved": glu_flops / (glu_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": glu_flops / (glu_ms * 1e-3) / 1e12 / peak_tf, "ms_per_launch": glu_ms,
+                "algorithmic_flops_per_launch": glu_flops, "peak_source": peak_src,
+                "note": "L2 flushed before each launch: weights and the G tile come from HBM"},
+            "cpu_baseline": {"value": cpu_v, "unit": "windows/s", "cores": threads, "kind": ref.kind,
                              "sample": f"{cpu_steps} eval forwards of one {B}-window batch "
                                        f"({cpu_ms:.1f} ms each); os.cpu_count()={os.cpu_count()}"},
             "clocks": clocks}
     print(json.dumps(line), flush=True)
+
+
+def forward_flops(B, N, W, H, S=2, K=4):
+    """SURVEY.md §8(d) dead-work-free forward flops."""
+    T = MULTI * W
+    d = K * T
+    blk = (2 * (K - 1) * B * N * N * W + 2 * B * N * d * 2 * (36 + 30) * W / 12 + 2 * B * N * d * d * 4 +
+           2 * B * N * d * 2 * (124 + 116) * T / 60 + 2 * K * B * N * T * T + 2 * B * N * (T * T + T * W))
+    return float(6 * B * N * N * W + 6 * B * N ** 3 + 12 * B * N * N + 10 * B * N * N + 4 * N ** 3 + 6 * N * N +
+                 S * blk + 2 * B * N * (T * W + W * W) + 2 * B * N * (W * W + W * H))
+
+
+def time_glu_chain(lib, dev, B, N, W, flush):
+    """One launch of the fused 3-layer GLU chain kernel (K1 = 3W -> d -> d -> d over B*N rows), CUDA events."""
+    import torch
+    if not hasattr(lib, "stemgnn_glu_chain"):
+        return None, None
+    R, d, K1 = B * N, 4 * MULTI * W, 3 * W
+    g = torch.Generator().manual_seed(5)
+    G = torch.randn(R, K1, generator=g).to(dev)
+    ws = [torch.randn(d, K1 if l == 0 else d, generator=g).div_((K1 if l == 0 else d) ** 0.5).to(dev)
+          for l in range(3) for _ in range(2)]
+    bs = [torch.zeros(d, device=dev) for _ in range(6)]
+    out = torch.empty(R, d, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    wp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in ws])
+    bp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bs])
+
+    def call():
+        rc = lib.stemgnn_glu_chain(R, d, K1, G.data_ptr(), K1, wp, bp, out.data_ptr(), d, 0, st)
+        if rc:
+            raise RuntimeError(lib.stemgnn_last_error().decode())
+    for _ in range(3):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot, reps = 0.0, 10
+    for _ in range(reps):
+        flush.zero_()
+        e0.record(); call(); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    flops = 2.0 * R * 2 * d * (K1 + d + d)
+    return tot / reps, flops
+
+
+def time_train_step(model, x_dev, y_dev, flush, barrier, steps, world):
+    """zero_grad + forward (train mode, Philox dropout) + MSE + backward (+ the single flat-gradient all-reduce
+    at N>1) + RMSprop: through the captured-graph trainer when the package has one, else eager torch."""
+    import torch
+    from stemgnn_b200 import ddp
+    ddp.attach(model)
+    model.train()
+    what = "zero_grad + forward(train, Philox dropout) + MSE + backward" + \
+        (" + flat-gradient NCCL all-reduce" if world > 1 else "") + " + RMSprop step"
+    try:
+        from stemgnn_b200.trainer import FusedTrainer
+        tr = FusedTrainer(model, optimizer="RMSProp", lr=1e-4)
+        step = lambda: tr.step(x_dev, y_dev)                       # noqa: E731
+        what += " — one CUDA graph replay (stemgnn_b200.trainer.FusedTrainer, fused RMSprop kernel, no host sync)"
+    except ImportError:
+        optim = torch.optim.RMSprop(model.parameters(), lr=1e-4, eps=1e-8)
+        crit = torch.nn.MSELoss()
+
+        def step():
+            model.zero_grad()
+            f, _a = model(x_dev)
+            loss = crit(f, y_dev)
+            loss.backward()
+            optim.step()
+    t_steps = max(5, min(steps, 20))
+    for _ in range(3):
+        step()
+    tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(t_steps)]
+    barrier()
+    for i in range(t_steps):
+        flush.zero_()
+        tev[i][0].record()
+        step()
+        tev[i][1].record()
+    barrier()
+    return {"total_ms": sum(a.elapsed_time(b) for a, b in tev), "steps": t_steps, "what": what}
 
 
 def main():
@@ -371,6 +465,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

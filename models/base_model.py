@@ -66,6 +66,11 @@ class StockBlockLayer(nn.Module):
             self.GLUs.append(GLU(fan_in, d))    # real chain  (even index)
             self.GLUs.append(GLU(fan_in, d))    # imag chain  (odd index)
 
+    def __setstate__(self, state):
+        # a block unpickled from a REFERENCE-made whole-module checkpoint has no gemm_mode
+        self.__dict__.update(state)
+        self.__dict__.setdefault("gemm_mode", runtime.GEMM_FP32)
+
     # -- helpers ---------------------------------------------------------------------------------
     def _block_ptrs(self):
         prefix = f"stock_block.{self.stack_cnt}"
@@ -140,6 +145,7 @@ class Model(nn.Module):
         self.dropout = nn.Dropout(p=dropout_rate)
         self.gemm_mode = runtime.GEMM_AUTO
         self._dropout_calls = 0
+        self._philox_ctr = 0       # next free Philox block (dropout masks of successive steps never overlap)
         self._rt = None            # runtime cache (pointer struct, workspaces): never pickled
         self.to(device)
 
@@ -150,6 +156,20 @@ class Model(nn.Module):
         state.pop("_ddp", None)          # process groups are not picklable (whole-module checkpoints)
         return state
 
+    def __setstate__(self, state):
+        # also accepts the __dict__ of a module pickled by the REFERENCE class (handler.py:24 saves whole modules):
+        # fill what the reference object does not carry
+        self.__dict__.update(state)
+        d = self.__dict__
+        d.setdefault("_rt", None)
+        d.setdefault("gemm_mode", runtime.GEMM_AUTO)
+        d.setdefault("_dropout_calls", 0)
+        d.setdefault("_philox_ctr", 0)
+        if "dropout_rate" not in d:
+            drop = d.get("_modules", {}).get("dropout")
+            d["dropout_rate"] = float(getattr(drop, "p", 0.5))
+        self._rt = None
+
     def _apply(self, fn, *a, **kw):
         self._rt = None
         return super()._apply(fn, *a, **kw)
@@ -158,11 +178,20 @@ class Model(nn.Module):
         named = dict(self.named_parameters())
         return [named[k] for k in runtime.PARAM_KEYS]
 
+    def invalidate_runtime(self):
+        """Drops the cached pointer struct, workspaces and folded-weight state (call after writing parameters
+        through `.data`, which does not bump `._version`)."""
+        self._rt = None
+
     def _runtime(self):
-        if self._rt is None:
-            params = self._ordered_params()
+        # raw device pointers are cached: re-validate them on every call so that a replaced Parameter
+        # (`load_state_dict(assign=True)`, `p.data = ...`, `module.weight = nn.Parameter(...)`) can never leave
+        # stale pointers behind (ADVICE r1)
+        params = self._ordered_params()
+        sig = tuple((id(p), p.data_ptr()) for p in params)
+        if self._rt is None or self._rt["ptr_sig"] != sig:
             self._rt = {"params": params, "ptrs": runtime.build_ptrs(dict(zip(runtime.PARAM_KEYS, params))),
-                        "ptr_sig": tuple(p.data_ptr() for p in params), "ws": {}}
+                        "ptr_sig": sig, "ws": {}}
         return self._rt
 
     def _dims(self, B):
@@ -203,9 +232,11 @@ class Model(nn.Module):
         if ws is None:
             rt["ws"].clear()
             ws = rt["ws"][key] = runtime.alloc_workspace(dims, False, x.device)
-        rt["folded_for"] = (key, versions, self.gemm_mode)
+        rt["folded_for"] = None
         opts = runtime.make_opts(self.alpha, 0.0, False, gemm_mode=self.gemm_mode, reuse_folded=reuse)
-        return runtime.model_forward_raw(dims, rt["ptrs"], opts, x, ws, want_mul_L)
+        out = runtime.model_forward_raw(dims, rt["ptrs"], opts, x, ws, want_mul_L)
+        rt["folded_for"] = (key, versions, self.gemm_mode)       # only after a successful call
+        return out
 
     def forward(self, x, dropout_mask=None):
         """x: (B, W, N) float32 CUDA tensor.  `dropout_mask` (optional, tests): explicit {0,1}
@@ -228,7 +259,9 @@ class Model(nn.Module):
                 rank = (getattr(self, "_ddp", None) or {}).get("rank", 0)
                 seed = (seed + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF    # replicas draw different masks
                 self._dropout_calls += 1
-                offset = self._dropout_calls * ((x.shape[0] * self.unit * self.unit + 3) // 4 + 1)
+                # running Philox block counter: batches of different size (drop_last=False) never overlap
+                offset = self._philox_ctr = getattr(self, "_philox_ctr", 0) + 1
+                self._philox_ctr += (x.shape[0] * self.unit * self.unit + 3) // 4
             mask = None
             if dropout_mask is not None:
                 mask = dropout_mask.to(device=x.device, dtype=torch.uint8).contiguous()

@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE — not product code.
 
-Loads the UNMODIFIED reference (microsoft/StemGNN, mounted read-only at /root/reference)
-in this build container so that golden vectors can be minted from the reference itself.
-`/root/reference` does not exist on the GPU box: nothing that runs there imports this
-module (tests that need it skip when the directory is absent).
+Loads the UNMODIFIED reference (microsoft/StemGNN): mounted read-only at /root/reference in the
+build container (where the golden vectors are minted), or the byte-for-byte staged copy in the
+git-ignored `baseline/_ref/` (oracle/fetch_reference.py) — the copy that travels to the GPU box,
+where `bench.py --impl reference`, `cpu_baseline` and the reference-vs-CUDA tests use it.
 
 The reference pins torch==1.7.1 (requirements.txt:4) and uses four APIs that no longer
 exist on the container stack (torch 2.11 / numpy 2.3 / pandas 3.0).  They are patched
@@ -25,7 +25,20 @@ import importlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("STEMGNN_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root():
+    """Mounted reference in the build container, else the byte-for-byte staged copy that
+    `oracle/fetch_reference.py` puts in git-ignored baseline/_ref/ (the only copy the GPU box has)."""
+    cands = [os.environ.get("STEMGNN_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "models", "base_model.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -15,7 +15,18 @@ import runpy
 import sys
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-REF = os.environ.get("STEMGNN_REFERENCE_ROOT", "/root/reference")
+
+
+def _reference_root():
+    """The mounted reference, else the staged byte-for-byte copy (git-ignored baseline/_ref/, see
+    oracle/fetch_reference.py) — the GPU box only has the latter."""
+    for c in (os.environ.get("STEMGNN_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if c and os.path.isfile(os.path.join(c, "main.py")):
+            return c
+    return "/root/reference"
+
+
+REF = _reference_root()
 
 
 def main():

@@ -50,8 +50,11 @@ def allreduce_mean_(flat, group=None):
 def broadcast_parameters(module, src=0, group=None):
     """Replicas start from rank `src`'s parameters and buffers."""
     if world_size(group) > 1:
-        for t in list(module.parameters()) + list(module.buffers()):
-            dist.broadcast(t.data, src=src, group=group)
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t, src=src, group=group)     # in-place on the Parameter: bumps ._version
+        if hasattr(module, "invalidate_runtime"):
+            module.invalidate_runtime()                      # folded / pre-split weight caches are stale now
 
 
 def attach(model, group=None):

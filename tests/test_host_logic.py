@@ -288,3 +288,45 @@ int main(void) {
                           _lib.BlockPtrs.glu_left_w.offset, _lib.BlockPtrs.glu_right_b.offset]
     assert sizes[9:13] == [_lib.FwdOpts.dropout_seed.offset, _lib.FwdOpts.dropout_mask.offset,
                            _lib.FwdOpts.gemm_mode.offset, _lib.FwdOpts.reuse_folded.offset]
+
+
+def test_reference_made_module_pickle_loads_into_dropin(tmp_path):
+    """handler.py:24 saves WHOLE modules: a checkpoint written by the reference class must unpickle into the
+    drop-in class of the same module path and be usable (__setstate__ fills what the reference lacks)."""
+    import pickle
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference not available")
+    with ref_shim.reference_modules():
+        import importlib
+        cls = importlib.import_module("models.base_model").Model
+        torch.manual_seed(0)
+        blob = pickle.dumps(cls(10, 2, 12, 5, horizon=3))
+    import models.base_model as ours          # the repo's drop-in is back in sys.modules here
+    m = pickle.loads(blob)
+    assert type(m) is ours.Model and type(m.stock_block[1]) is ours.StockBlockLayer
+    assert m._rt is None and m.gemm_mode == 0 and m.dropout_rate == 0.5 and m.multi_layer == 5
+    assert m.stock_block[0].gemm_mode == 1
+    with pytest.raises(RuntimeError, match="CUDA"):          # reaches the runtime, which refuses CPU tensors
+        m(torch.zeros(2, 12, 10))
+
+
+def test_runtime_cache_follows_replaced_parameters():
+    """the cached raw-pointer struct is rebuilt when a Parameter object or its storage is replaced."""
+    from models.base_model import Model
+    import torch.nn as nn
+    m = Model(6, 2, 12, 5, horizon=3)
+    seen = []
+    import stemgnn_b200.runtime as rt
+    orig = rt.build_ptrs
+    try:
+        rt.build_ptrs = lambda tensors: seen.append(tensors["weight_key"].data_ptr()) or object()
+        r1 = m._runtime()
+        assert m._runtime() is r1 and len(seen) == 1                      # cached while nothing changes
+        m.weight_key = nn.Parameter(torch.ones(6, 1))
+        r2 = m._runtime()
+        assert r2 is not r1 and seen[-1] == m.weight_key.data_ptr()
+        m.weight_query.data = torch.zeros(6, 1)
+        assert m._runtime() is not r2
+    finally:
+        rt.build_ptrs = orig
