@@ -115,6 +115,7 @@ long long stemgnn_launch_count(void);      /* kernels launched by this library s
 /* Measurement hook: when both are non-NULL cudaEvent_t, every following forward records them on its
  * stream immediately before / after the GRU recurrence kernel (the dominant launch); NULL disables. */
 void stemgnn_profile_gru(void* start_event, void* stop_event);
+const char* stemgnn_gru_kernel_name(void); /* description of the recurrence kernel the default path launches */
 
 /* Bytes of caller-provided workspace needed by stemgnn_model_forward / _backward for `dims`.
  * The SAME buffer must be passed to the backward of a training forward (it holds the saved
@@ -146,7 +147,8 @@ int stemgnn_model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p
  *      the parity tests; same kernels as the fused path) ------------------------------------ */
 /* nn.GRU over the node axis + key/query contraction (base_model.py:137,154-155).
  *   x (B,W,N) -> key (B,N), query (B,N); gru_out (N,B,N) optional (NULL to skip).
- *   path: 0 = auto, 1 = force the generic (per-step launch) path, 2 = force the cluster path. */
+ *   path: 0 = auto (tensor-core recurrence, else FFMA2 cluster kernel, else per-step), 1 = force the generic
+ *   (per-step launch) path, 2 = force the fp32 FFMA2 cluster kernel, 3 = force the tcgen05 recurrence. */
 int stemgnn_gru_keyquery_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
                                  const float* x, float* key, float* query, float* gru_out,
                                  int path, void* workspace, size_t workspace_bytes,

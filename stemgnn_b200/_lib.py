@@ -44,6 +44,7 @@ SYMBOLS = {
     "stemgnn_device_ok": (c_int, []),
     "stemgnn_launch_count": (ctypes.c_longlong, []),
     "stemgnn_profile_gru": (None, [c_void_p, c_void_p]),
+    "stemgnn_gru_kernel_name": (c_char_p, []),
     "stemgnn_workspace_bytes": (c_size_t, [POINTER(Dims), c_int]),
     "stemgnn_model_forward": (c_int, [POINTER(Dims), POINTER(ModelPtrs), POINTER(FwdOpts), c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

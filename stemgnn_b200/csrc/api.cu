@@ -291,6 +291,7 @@ int stemgnn_version(void) { return STEMGNN_ABI_VERSION; }
 const char* stemgnn_last_error(void) { return g_err; }
 
 long long stemgnn_launch_count(void) { return g_launches; }
+const char* stemgnn_gru_kernel_name(void) { return gru_tc_kernel_name(); }
 
 void stemgnn_profile_gru(void* start_event, void* stop_event) {
   g_hook.start = static_cast<cudaEvent_t>(start_event);
@@ -329,6 +330,7 @@ int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
   SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dm.B, dm.W, dm.N, st));
   GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
                 p->weight_query, ws.key, ws.query, ws.h_all, ws.gi, ws.g_r, ws.g_z, ws.g_n, ws.g_hn, dm.B, dm.N, dm.W};
+  ga.tc_reuse = (opts->reuse_folded && !opts->training) ? 1 : 0;
   SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
   SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
   SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, opts->reuse_folded && !opts->training, ws.x_bnw, x,

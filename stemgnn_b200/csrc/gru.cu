@@ -1068,6 +1068,13 @@ int gru_keyquery_forward(const GruArgs& a_in, int path, float* scratch, cudaStre
   SG_CHECK(a.B > 0 && a.N > 0 && a.W > 0, "gru: bad dims B=%d N=%d W=%d", a.B, a.N, a.W);
   a.xrep = 1;
   if (const char* e = getenv("STEMGNN_GRU_XREP")) a.xrep = atoi(e) > 0 ? atoi(e) : 1;
+  if (path == 0 || path == 3) {
+    // tensor-core recurrence (gru_tc.cu): input projection in-kernel, packed W_hh images live at the start of `gi`
+    const int rc = gru_tc_forward(a, reinterpret_cast<uint8_t*>(a.gi), a.tc_reuse, st);
+    if (rc == 0) return 0;
+    if (rc > 0) return rc;
+    SG_CHECK(path != 3, "gru: tensor-core path unavailable for N=%d W=%d on this device", a.N, a.W);
+  }
   SG_TRY(gru_input_proj(a, st));
   if (path != 1) {
     // 16-CTA clusters with one group of 4 (or 5, to stay within the 7 resident clusters of a B200)

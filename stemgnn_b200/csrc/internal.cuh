@@ -20,7 +20,12 @@ struct GruArgs {
   float* g_r; float* g_z; float* g_n; float* g_hn;   // (N, B, N) gate values saved for BPTT (or null)
   int B, N, W;
   int xrep;            // measurement knob: redundant DSMEM sends per step (1 = normal)
+  int tc_reuse;        // 1: the packed fp16 hi/lo W_hh images at the start of `gi` are still valid (frozen weights)
 };
+// tensor-core recurrence (gru_tc.cu): 0 launched, -1 outside its envelope (caller falls back), >0 error
+int gru_tc_forward(const GruArgs& a, uint8_t* img, int reuse_img, cudaStream_t st);
+size_t gru_tc_image_bytes(int N, int W);
+const char* gru_tc_kernel_name();
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
 // persistent-cluster BPTT (one launch); -1 = unsupported here, use the per-step kernels
 int gru_bwd_cluster(const float* w_hh, const float* wk, const float* wq, const float* d_key,

@@ -78,7 +78,7 @@ def _gru_call(c, path):
     return x, p, key, query, out
 
 
-@pytest.mark.parametrize("path", [2, 1], ids=["cluster", "generic"])
+@pytest.mark.parametrize("path", [3, 2, 1], ids=["tensorcore", "cluster", "generic"])
 @pytest.mark.parametrize("name", ["tiny_taps", "odd_h1_taps", "multi2_w8", "cfg1_trained", "cfg2_shape"])
 def test_gru_keyquery_vs_oracle(name, path):
     c = cases("forward")[name]
@@ -95,10 +95,11 @@ def test_gru_keyquery_vs_oracle(name, path):
         assert_close(out, golden(name)["gru_out"], rtol=1e-4, atol=2e-6, msg="gru_out vs reference golden")
 
 
-def test_gru_ragged_batch_and_padding():
-    """B not a multiple of the 4-sequence cluster group; N not a multiple of 16."""
+@pytest.mark.parametrize("path", [3, 2], ids=["tensorcore", "cluster"])
+def test_gru_ragged_batch_and_padding(path):
+    """B not a multiple of the sequences-per-cluster group; N not a multiple of the unit slice."""
     c = dict(B=7, N=53, W=12, H=3, multi=5, pseed=77, mode="trained")
-    x, p, key, query, out = _gru_call(c, 2)
+    x, p, key, query, out = _gru_call(c, path)
     pc = {k: v.cpu() for k, v in p.items()}
     with torch.no_grad():
         ref = tp._gru(x.permute(2, 0, 1).contiguous(), pc)
