@@ -179,6 +179,17 @@ int stemgnn_spe_seq_cell_forward(const stemgnn_dims_t* dims, const stemgnn_block
 int stemgnn_gather_windows(const float* series, int T, int N, const int32_t* end_idx, int B, int W, int H,
                            float* x, float* y, stemgnn_stream_t stream);
 
+/* Validation metrics on the device (reference: models/handler.py:74-82 validate, data_loader/forecast_dataloader.py:25-38
+ * de_normalized, utils/math_utils.py:24-74 evaluate).  forecast_norm (count,H,N) float64 and target_norm (count,H,N)
+ * float32 are the NORMALISED tensors; method 0 = none, 1 = z_score (scale = std with 0 -> 1, shift = mean),
+ * 2 = min_max (scale = max - min + 1e-8, shift = min).  sums (6,N) float64 out: per node
+ * [sum clip(|e|/|y|+1e-5, 5), sum |e|, sum e^2] on the de-normalised values, then the same three on the normalised
+ * values; every metric of `evaluate` (overall and by_node) is a mean / sqrt-mean of these.  partial: scratch of
+ * chunks*6*N doubles (two-stage, fixed-order reduction: results are deterministic). */
+int stemgnn_eval_metrics(const double* forecast_norm, const float* target_norm, long long count, int H, int N,
+                         int method, const double* scale, const double* shift, double* partial, int chunks,
+                         double* sums, stemgnn_stream_t stream);
+
 /* C[M,N] = alpha * A(M,K) * B(K,N) + beta * C  on the library's fp32 FFMA2 GEMM (test hook).
  * a_kmajor: 0 -> A[m*lda+k], 1 -> A[k*lda+m];  b_nk: 1 -> B[n*ldb+k] (nn.Linear weight), 0 -> B[k*ldb+n]. */
 int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int a_kmajor,

@@ -50,7 +50,7 @@ def load_model(model_dir, epoch=None):
         return torch.load(f, weights_only=False)
 
 
-def inference(model, dataloader, device, node_cnt, window_size, horizon):
+def _inference_tensors(model, dataloader, device, node_cnt, window_size, horizon):
     """Rolling forecast: the model emits `len_out` steps per call; the window is shifted by the
     prediction until `horizon` steps exist (one call per batch when the model emits the full
     horizon).  Returns (forecast, target) numpy arrays of shape (count, horizon, node).
@@ -75,24 +75,43 @@ def inference(model, dataloader, device, node_cnt, window_size, horizon):
                 done += take
             forecasts.append(steps)
             targets.append(target.detach())
-    return torch.cat(forecasts, dim=0).cpu().numpy(), torch.cat(targets, dim=0).cpu().numpy()
+    return torch.cat(forecasts, dim=0), torch.cat(targets, dim=0)
+
+
+def inference(model, dataloader, device, node_cnt, window_size, horizon):
+    """Reference signature (handler.py:41-71): (forecast, target) numpy arrays of shape (count, horizon, node)."""
+    f, t = _inference_tensors(model, dataloader, device, node_cnt, window_size, horizon)
+    return f.cpu().numpy(), t.cpu().numpy()
 
 
 def validate(model, dataloader, device, normalize_method, statistic, node_cnt, window_size, horizon,
              result_file=None):
-    forecast_norm, target_norm = inference(model, dataloader, device, node_cnt, window_size, horizon)
-    if normalize_method and statistic:
-        forecast = de_normalized(forecast_norm, normalize_method, statistic)
-        target = de_normalized(target_norm, normalize_method, statistic)
+    f_dev, t_dev = _inference_tensors(model, dataloader, device, node_cnt, window_size, horizon)
+    if f_dev.is_cuda and os.environ.get('STEMGNN_HOST_METRICS') is None:
+        # de-normalisation + MAPE/MAE/RMSE reductions on the device: one D2H copy of (6, N) float64 per validation
+        # (reference: de_normalized + 3 x evaluate in numpy on the host, handler.py:74-82)
+        from stemgnn_b200.metrics import device_evaluate
+        score, score_by_node, score_norm = device_evaluate(f_dev, t_dev, normalize_method, statistic)
+        forecast = target = None
     else:
-        forecast, target = forecast_norm, target_norm
-    score = evaluate(target, forecast)
-    score_by_node = evaluate(target, forecast, by_node=True)
-    score_norm = evaluate(target_norm, forecast_norm)
+        forecast_norm, target_norm = f_dev.cpu().numpy(), t_dev.cpu().numpy()
+        if normalize_method and statistic:
+            forecast = de_normalized(forecast_norm, normalize_method, statistic)
+            target = de_normalized(target_norm, normalize_method, statistic)
+        else:
+            forecast, target = forecast_norm, target_norm
+        score = evaluate(target, forecast)
+        score_by_node = evaluate(target, forecast, by_node=True)
+        score_norm = evaluate(target_norm, forecast_norm)
     print(f'NORM: MAPE {score_norm[0]:7.9%}; MAE {score_norm[1]:7.9f}; RMSE {score_norm[2]:7.9f}.')
     print(f'RAW : MAPE {score[0]:7.9%}; MAE {score[1]:7.9f}; RMSE {score[2]:7.9f}.')
     if result_file:
         os.makedirs(result_file, exist_ok=True)
+        if forecast is None:         # the CSV dumps need the first-step rows on the host (test() only)
+            f0, t0 = f_dev[:, :1, :].cpu().numpy(), t_dev[:, :1, :].cpu().numpy()
+            if normalize_method and statistic:
+                f0, t0 = de_normalized(f0, normalize_method, statistic), de_normalized(t0, normalize_method, statistic)
+            forecast, target = f0, t0
         pred, truth = forecast[:, 0, :], target[:, 0, :]
         np.savetxt(f'{result_file}/target.csv', truth, delimiter=",")
         np.savetxt(f'{result_file}/predict.csv', pred, delimiter=",")

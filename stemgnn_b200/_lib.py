@@ -61,6 +61,8 @@ SYMBOLS = {
                                              c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemgnn_gather_windows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p]),
+    "stemgnn_eval_metrics": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_int, c_void_p, c_void_p]),
     "stemgnn_sgemm": (c_int, [c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_float, c_void_p, c_int, c_void_p]),
     "stemgnn_glu_gemm": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

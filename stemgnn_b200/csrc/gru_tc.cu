@@ -77,6 +77,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 24)) __trap();   // a lost signal must fail loudly, never hang the GPU
   }
 }
+// wait on a barrier that is completed by st.async stores of OTHER CTAs of the cluster: acquire at cluster scope
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = s_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(s_u32(bar))
@@ -279,6 +294,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
     }
     bias_sm[i] = v;
   }
+  if (ta.x_smem) {                     // the cluster's input rows x[s][b0 .. b0+nb) -> smem (16-byte loads, W % 4 == 0)
+    const int rowv = nb * W / 4, pitch = G * W / 4;
+    const float4* src = reinterpret_cast<const float4*>(a.xs);
+    float4* dst = reinterpret_cast<float4*>(xs_sm);
+    for (int idx = tid; idx < N * rowv; idx += GT_THREADS) {
+      const int ss = idx / rowv, v = idx - ss * rowv;
+      dst[(size_t)ss * pitch + v] = __ldg(src + ((size_t)ss * B + b0) * (W / 4) + v);
+    }
+  }
   fence_async_proxy();                 // generic-proxy zero fill -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
@@ -303,12 +327,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       }
       rdy_sm[lane] = mask;
       rdy_sm[8 + lane] = (uint32_t)last;
-    }
-    if (lane == 0 && ta.x_smem) {      // the cluster's input rows: one bulk copy per step (nb * W floats)
-      const uint32_t row_bytes = (uint32_t)(nb * W * 4);
-      mbar_expect_tx(xbar, row_bytes * (uint32_t)N);
-      for (int s = 0; s < N; ++s)
-        bulk_g2s(xs_sm + (size_t)s * G * W, a.xs + ((size_t)s * B + b0) * W, row_bytes, xbar);
     }
     __syncwarp();
   } else if (warp >= GT_ROUNDS) {
@@ -356,7 +374,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
         const uint32_t par = (uint32_t)((s - 1) >> 1) & 1u;
         const bool dbg_on = ta.dbg != nullptr && blockIdx.x == 0 && lane == 0 && r == GT_ROUNDS - 1 && s >= dbg_s0 && s < dbg_s0 + 4;
         GT_STAMP(0);
-        if (lane <= last) mbar_wait(&hbar[cur * 16 + my_p], par);      // slices of h_{s-1} landed in B[cur]
+        if (lane <= last) {
+          mbar_wait_cluster(&hbar[cur * 16 + my_p], par);              // slices of h_{s-1} landed in B[cur]
+          fence_async_proxy();         // every observer orders the remote generic-proxy stores before async-proxy reads
+        }
         __syncwarp();
         GT_STAMP(1);
         if (elect_one()) {
@@ -430,7 +451,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
         }
       }
     };
-    if (ta.x_smem) mbar_wait(xbar, 0);
 #pragma unroll
     for (int i = 0; i < PP; ++i) input_proj(0, i, gi_r[i], gi_z[i], gi_n[i]);
 

@@ -55,7 +55,42 @@ def one(B, N, W, path, reps):
     print(msg, flush=True)
 
 
+def stress(B, N, W, calls):
+    """Race detector: `calls` independent forwards with gru_out, every result compared with the host GRU."""
+    import torch
+    from stemgnn_b200 import _lib as L, runtime, synthetic as sy
+    from oracle import torch_port as tp
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    p = sy.synthetic_params(N, W, 3, 5, seed=N, scale_mode="trained")
+    x, _ = sy.synthetic_batch(B, N, W, 3, seed=7)
+    pd = {k: v.to(dev) for k, v in p.items()}
+    dims = L.Dims(B, N, W, 3, 5)
+    ptrs = runtime.build_ptrs({k: pd.get(k) for k in runtime.PARAM_KEYS})
+    ws = runtime.alloc_workspace(dims, False, dev)
+    xd = x.to(dev)
+    key = torch.empty(B, N, device=dev); query = torch.empty(B, N, device=dev); out = torch.empty(N, B, N, device=dev)
+    with torch.no_grad():
+        ref = tp._gru(x.permute(2, 0, 1).contiguous(), p).to(dev)
+    errs = []
+    junk = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    for i in range(calls):
+        if i % 3 == 1:
+            junk.zero_()                      # perturb timing / cache state
+        rc = lib.stemgnn_gru_keyquery_forward(ctypes.byref(dims), ctypes.byref(ptrs), xd.data_ptr(), key.data_ptr(),
+                                              query.data_ptr(), out.data_ptr() if i % 2 == 0 else None, 3, ws.data_ptr(),
+                                              ws.numel(), runtime._stream_ptr(dev))
+        L.check(rc, "gru")
+        if i % 2 == 0:
+            errs.append(float((out - ref).abs().max()))
+    bad = [e for e in errs if e > 4e-6]
+    print(f"stress B={B} N={N}: {len(errs)} checked calls, max err {max(errs):.3e}, {len(bad)} above 4e-6", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "stress":
+        stress(*[int(v) for v in sys.argv[2:6]])
+        sys.exit(0)
     if len(sys.argv) > 1:
         B, N, W, path, reps = [int(v) for v in sys.argv[1:6]]
         one(B, N, W, path, reps)
