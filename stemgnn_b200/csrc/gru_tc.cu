@@ -208,8 +208,12 @@ struct GruTcArgs {
   int x_smem;             // 1: the cluster's x rows are staged in shared memory by bulk copies
   int pipelined;          // 1: MMAs of a K range start as soon as its source CTAs' slices landed
   long long* dbg;         // optional clock64 stamps (STEMGNN_GRU_TC_DBG), null in production
+  int dbg_mode;           // 1 both, 2 epilogue stamps only, 3 MMA-warp stamps only
+  int xmode;              // experiment knob (STEMGNN_GRU_TC_X): 1 generic read-back before the MMAs, 2 lo granules first, 3 every lane waits on every barrier
 };
-#define GT_STAMP(slot) do { if (dbg_on) ta.dbg[(s - dbg_s0) * 16 + (slot)] = clock64(); } while (0)
+// stamps are taken under a WARP-UNIFORM condition and the warp is re-converged right after: a lane that diverges in front of
+// elect.sync / tcgen05.ld.sync.aligned breaks those warp-collective instructions (seen as wrong results in early debug builds)
+#define GT_STAMP(slot) do { if (dbg_on) { if (lane == 0) ta.dbg[(s - dbg_s0) * 16 + (slot)] = clock64(); __syncwarp(); } } while (0)
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
   asm volatile(
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
   // ---- one-time setup ------------------------------------------------------------------------------------
   if (tid == 0) {
     for (int i = 0; i < 2 * 16; ++i) mbar_init(&hbar[i], 1);
-    for (int r = 0; r < GT_ROUNDS; ++r) mbar_init(&tfull[r], 1);
+    for (int r = 0; r < GT_ROUNDS; ++r) mbar_init(&tfull[r], 1);   // tfull[0] is re-initialised below with the round count
     mbar_init(xbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -316,8 +320,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       uint32_t mask = 0;
       int last = -1, prev_last = -1;
       if (lane < R) {
-        last = ((lane + 1) * CS + R - 1) / R - 1;
-        prev_last = lane == 0 ? -1 : (lane * CS + R - 1) / R - 1;
+        // even split: a step is bound by the tensor pipe (2 NKS instructions at ~22 cycles) once the first slices are in, so the
+        // rounds only need to start early; what matters is that round 0 can begin after a third of the arrivals
+        auto last_of = [&](int rr) { return ((rr + 1) * CS + R - 1) / R - 1; };
+        last = last_of(lane);
+        prev_last = lane == 0 ? -1 : last_of(lane - 1);
         if (!ta.pipelined) { last = lane == 0 ? CS - 1 : -1; prev_last = lane == 0 ? -1 : CS; }
         for (int j = 0; j < g.NKS; ++j) {
           const int p0 = (16 * j) / U, p1 = min((16 * j + 15) / U, CS - 1);
@@ -327,6 +334,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       }
       rdy_sm[lane] = mask;
       rdy_sm[8 + lane] = (uint32_t)last;
+      const uint32_t nz = __ballot_sync((1u << GT_ROUNDS) - 1u, mask != 0u);
+      if (lane == 0) {                 // ONE accumulator barrier: every non-empty round commits to it once per step
+        rdy_sm[12] = (uint32_t)__popc(nz);
+        if (nz != 0u) {
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(s_u32(&tfull[0])) : "memory");
+          mbar_init(&tfull[0], (uint32_t)__popc(nz));
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+      }
     }
     __syncwarp();
   } else if (warp >= GT_ROUNDS) {
@@ -372,13 +388,27 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       for (int s = 1; s < N; ++s) {
         const int cur = s & 1;
         const uint32_t par = (uint32_t)((s - 1) >> 1) & 1u;
-        const bool dbg_on = ta.dbg != nullptr && blockIdx.x == 0 && lane == 0 && r == GT_ROUNDS - 1 && s >= dbg_s0 && s < dbg_s0 + 4;
+        const bool dbg_on = ta.dbg != nullptr && ta.dbg_mode != 2 && blockIdx.x == 0 && r == GT_ROUNDS - 1 && s >= dbg_s0 && s < dbg_s0 + 4;
         GT_STAMP(0);
-        if (lane <= last) {
+        if (ta.xmode == 3) {
+          for (int i = 0; i <= last; ++i) mbar_wait_cluster(&hbar[cur * 16 + (q - i + 16 * CS) % CS], par);
+          fence_async_proxy();
+        } else if (lane <= last) {
           mbar_wait_cluster(&hbar[cur * 16 + my_p], par);              // slices of h_{s-1} landed in B[cur]
           fence_async_proxy();         // every observer orders the remote generic-proxy stores before async-proxy reads
         }
         __syncwarp();
+        if (ta.xmode == 1) {           // generic-proxy read-back of the whole tile, then the proxy fence
+          const uint4* bt = reinterpret_cast<const uint4*>(B_sm + (size_t)cur * b_buf);
+          uint32_t acc = 0;
+          for (int i = lane; i < (int)(b_buf / 16); i += 32) {
+            const uint4 v = *reinterpret_cast<const volatile uint4*>(bt + i);
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+          }
+          asm volatile("" ::"r"(acc));
+          fence_async_proxy();
+          __syncwarp();
+        }
         GT_STAMP(1);
         if (elect_one()) {
           fence_async_proxy();
@@ -393,7 +423,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
             umma_f16_ts(d0 + 16u, a_lo + (uint32_t)j * 8u, bd, acc);       // W_lo . [h_hi | h_lo]
             acc = 1u;
           }
-          umma_commit(&tfull[r]);
+          umma_commit(&tfull[0]);
         }
         __syncwarp();
         GT_STAMP(3);
@@ -469,7 +499,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       if (idx < n_send) {
         const int slot = idx / n_gran, gr = idx - slot * n_gran;
         const int dest = (q + slot) % CS;
-        const int arr = gr / (G * gran_per_b), rem = gr - arr * (G * gran_per_b);
+        int arr = gr / (G * gran_per_b);
+        const int rem = gr - arr * (G * gran_per_b);
+        if (ta.xmode == 2) arr ^= 1;
         const int bb = rem / gran_per_b, g8 = rem - bb * gran_per_b;
         snd_src[it] = (uint32_t)(((arr * GT_GMAX + bb) * U + 8 * g8) * 2);                  // bytes into stage_sm
         const uint32_t off = sw128_off(arr * 8 + bb, u0 + 8 * g8, B_CHUNK_BYTES);
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
     const int dbg_s0 = N / 2;
     for (int s = 0; s < N; ++s) {
       const int nxt = (s & 1) ^ 1;
-      const bool dbg_on = ta.dbg != nullptr && blockIdx.x == 0 && et == 0 && s >= dbg_s0 && s < dbg_s0 + 4;
+      const bool dbg_on = ta.dbg != nullptr && ta.dbg_mode != 3 && blockIdx.x == 0 && warp == GT_ROUNDS && s >= dbg_s0 && s < dbg_s0 + 4;
       GT_STAMP(4);
       if (et < CS && s + 1 < N) mbar_expect_tx(&hbar[nxt * 16 + et], src_bytes);   // arm the tile that will receive h_s
       // input projection of the NEXT step while this step's MMAs run
@@ -500,12 +532,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
         float o[8];
 #pragma unroll
         for (int b = 0; b < 8; ++b) o[b] = 0.f;
+        mbar_wait(&tfull[0], (uint32_t)(s - 1) & 1u);      // every round's MMAs of this step are complete
+        tc_fence_after();
+        GT_STAMP(6);
 #pragma unroll
         for (int r = 0; r < GT_ROUNDS; ++r) {
           if (rdy_sm[r] != 0u) {
-            mbar_wait(&tfull[r], (uint32_t)(s - 1) & 1u);
-            tc_fence_after();
-            if (r == GT_ROUNDS - 1) GT_STAMP(6);
             float d[32];
             tmem_ld32(taddr + 32u * (uint32_t)r, d);
             tmem_ld_wait();
@@ -680,6 +712,8 @@ int gru_tc_forward(const GruArgs& a, uint8_t* img, int reuse_img, cudaStream_t s
   ta.pipelined = no_pipe ? 0 : 1;
   ta.x_smem = 0;
   static const bool dbg = getenv("STEMGNN_GRU_TC_DBG") != nullptr;
+  ta.dbg_mode = dbg ? atoi(getenv("STEMGNN_GRU_TC_DBG")) : 0;
+  ta.xmode = getenv("STEMGNN_GRU_TC_X") ? atoi(getenv("STEMGNN_GRU_TC_X")) : 0;
   static long long* dbg_buf = nullptr;
   if (dbg) {
     if (dbg_buf == nullptr) SG_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));

@@ -84,8 +84,8 @@ def test_gru_keyquery_vs_oracle(name, path):
     c = cases("forward")[name]
     x, p, key, query, out = _gru_call(c, path)
     pc = {k: v.cpu() for k, v in p.items()}
-    with torch.no_grad():
-        ref = tp._gru(x.permute(2, 0, 1).contiguous(), pc)          # (S,B,H), aten::gru on CPU
+    with torch.no_grad():   # (S,B,H) aten::gru on the host in float64 (independent of the host BLAS's fp32 code path)
+        ref = tp._gru(x.permute(2, 0, 1).contiguous().double(), {k: v.double() for k, v in pc.items()}).float()
     ref_key = torch.einsum("sbh,s->bh", ref.double(), pc["weight_key"][:, 0].double()).float()
     ref_query = torch.einsum("sbh,s->bh", ref.double(), pc["weight_query"][:, 0].double()).float()
     assert_close(out, ref, rtol=1e-4, atol=2e-6, msg="gru_out")
@@ -102,8 +102,38 @@ def test_gru_ragged_batch_and_padding(path):
     x, p, key, query, out = _gru_call(c, path)
     pc = {k: v.cpu() for k, v in p.items()}
     with torch.no_grad():
-        ref = tp._gru(x.permute(2, 0, 1).contiguous(), pc)
+        ref = tp._gru(x.permute(2, 0, 1).contiguous().double(), {k: v.double() for k, v in pc.items()}).float()
     assert_close(out, ref, rtol=1e-4, atol=2e-6, msg="gru_out ragged")
+
+
+@pytest.mark.parametrize("B,N", [(32, 358), (64, 228), (33, 325)])
+def test_gru_tensorcore_repeatability(B, N):
+    """The tcgen05 recurrence exchanges h through DSMEM with mbarrier-signalled st.async stores: 40 back-to-back calls
+    (with cache-perturbing work in between) must all reproduce the host GRU — a lost or early signal shows up here."""
+    c = dict(B=B, N=N, W=12, H=3, multi=5, pseed=N, mode="trained")
+    from stemgnn_b200 import runtime
+    L, lib = _lib()
+    p = case_params(c, DEV)
+    x, _ = tp.synthetic_batch(B, N, 12, 3, seed=7)
+    xd = x.to(DEV)
+    dims = L.Dims(B, N, 12, 3, 5)
+    ptrs = runtime.build_ptrs({k: p.get(k) for k in runtime.PARAM_KEYS})
+    ws = runtime.alloc_workspace(dims, False, xd.device)
+    key = torch.empty(B, N, device=DEV); query = torch.empty(B, N, device=DEV); out = torch.empty(N, B, N, device=DEV)
+    pc = {k: v.cpu().double() for k, v in p.items()}
+    with torch.no_grad():
+        ref = tp._gru(x.permute(2, 0, 1).contiguous().double(), pc).float().to(DEV)
+    junk = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
+    worst = 0.0
+    for i in range(40):
+        if i % 3 == 1:
+            junk.zero_()
+        rc = lib.stemgnn_gru_keyquery_forward(ctypes.byref(dims), ctypes.byref(ptrs), xd.data_ptr(), key.data_ptr(),
+                                              query.data_ptr(), out.data_ptr(), 3, ws.data_ptr(), ws.numel(),
+                                              runtime._stream_ptr(xd.device))
+        L.check(rc, "gru")
+        worst = max(worst, float((out - ref).abs().max()))
+    assert worst < 3e-6, worst
 
 
 # ---------------------------------------------------------------------------------------------
