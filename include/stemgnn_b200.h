@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STEMGNN_ABI_VERSION 1
+#define STEMGNN_ABI_VERSION 2
 #define STEMGNN_K 4            /* Chebyshev order "3 + 1", base_model.py:23 */
 #define STEMGNN_MAX_STACK 2    /* Model.forward hard-codes result[0] + result[1], base_model.py:174 */
 
@@ -105,6 +105,8 @@ typedef struct {
   int reuse_folded;         /* 1: the DFT-folded weights already in `workspace` (written by an earlier
                                forward with the SAME parameter values) are reused instead of being
                                recomputed — for inference loops with frozen weights */
+  const unsigned long long* dropout_offset_dev; /* optional DEVICE counter added to dropout_offset when the kernels run
+                               (NULL = none): lets a captured CUDA graph draw a fresh mask on every replay */
 } stemgnn_fwd_opts_t;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -189,6 +191,21 @@ int stemgnn_gather_windows(const float* series, int T, int N, const int32_t* end
 int stemgnn_eval_metrics(const double* forecast_norm, const float* target_norm, long long count, int H, int N,
                          int method, const double* scale, const double* shift, double* partial, int chunks,
                          double* sums, stemgnn_stream_t stream);
+
+/* ---- train-step tail on the device (reference: models/handler.py:160-166) ------------------------------------------ */
+/* MSELoss(reduction='mean') forward + backward: d_forecast[i] = 2 (forecast[i] - target[i]) / n and
+ * loss_accum[0] += mean((forecast - target)^2) (device scalar: no per-step host sync, handler.py:166). */
+int stemgnn_mse_loss_grad(const float* forecast, const float* target, long long n, float* d_forecast, float* loss_accum,
+                          stemgnn_stream_t stream);
+/* One fused optimiser launch over flat fp32 buffers of n elements.  kind 0 = RMSprop (torch.optim.RMSprop defaults:
+ * h0 = alpha, state1 = square_avg; handler.py:127), kind 1 = Adam (h0, h1 = betas, state1/2 = exp_avg / exp_avg_sq,
+ * bias correction with *step_dev + 1; handler.py:129).  lr_dev / step_dev are DEVICE scalars (graph-replay friendly). */
+int stemgnn_optimizer_step(int kind, float* params, const float* grads, float* state1, float* state2, long long n,
+                           const float* lr_dev, float h0, float h1, float eps, const unsigned long long* step_dev,
+                           stemgnn_stream_t stream);
+/* step_dev[0] += 1 and dropout_counter_dev[0] += dropout_inc (either pointer may be NULL). */
+int stemgnn_counters_tick(unsigned long long* step_dev, unsigned long long* dropout_counter_dev,
+                          unsigned long long dropout_inc, stemgnn_stream_t stream);
 
 /* C[M,N] = alpha * A(M,K) * B(K,N) + beta * C  on the library's fp32 FFMA2 GEMM (test hook).
  * a_kmajor: 0 -> A[m*lda+k], 1 -> A[k*lda+m];  b_nk: 1 -> B[n*ldb+k] (nn.Linear weight), 0 -> B[k*ldb+n]. */

@@ -153,11 +153,20 @@ def train(train_data, valid_data, args, result_file):
         with open(os.path.join(result_file, 'norm_stat.json'), 'w') as f:
             json.dump(normalize_statistic, f)
 
-    if args.optimizer == 'RMSProp':
-        optim = torch.optim.RMSprop(params=model.parameters(), lr=args.lr, eps=1e-08)
+    # On a CUDA device the step (zero_grad .. optimizer.step, handler.py:160-166 of the reference) is one captured CUDA
+    # graph with a fused optimiser kernel and a device-side loss accumulator (stemgnn_b200.trainer.FusedTrainer);
+    # STEMGNN_EAGER_TRAIN=1 keeps the reference's eager torch loop.
+    fused = None
+    if torch.device(args.device).type == 'cuda' and os.environ.get('STEMGNN_EAGER_TRAIN') is None:
+        from stemgnn_b200.trainer import FusedTrainer
+        fused = FusedTrainer(model, optimizer=args.optimizer, lr=args.lr, eps=1e-08, betas=(0.9, 0.999))
+        optim = scheduler = None
     else:
-        optim = torch.optim.Adam(params=model.parameters(), lr=args.lr, betas=(0.9, 0.999))
-    scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer=optim, gamma=args.decay_rate)
+        if args.optimizer == 'RMSProp':
+            optim = torch.optim.RMSprop(params=model.parameters(), lr=args.lr, eps=1e-08)
+        else:
+            optim = torch.optim.Adam(params=model.parameters(), lr=args.lr, betas=(0.9, 0.999))
+        scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer=optim, gamma=args.decay_rate)
 
     ds_kw = dict(window_size=args.window_size, horizon=args.horizon, normalize_method=args.norm_method,
                  norm_statistic=normalize_statistic)
@@ -173,18 +182,26 @@ def train(train_data, valid_data, args, result_file):
         loss_total, cnt = 0.0, 0
         for inputs, target in train_loader:
             inputs, target = inputs.to(args.device), target.to(args.device)
+            cnt += 1
+            if fused is not None:
+                fused.step(inputs, target)           # one graph replay; the loss stays on the device
+                continue
             model.zero_grad()
             forecast, _ = model(inputs)
             loss = criterion(forecast, target)
-            cnt += 1
             loss.backward()
             optim.step()
             loss_total += float(loss)
+        if fused is not None:
+            loss_total = fused.pop_loss()            # the epoch's only loss read-back
         print('| end of epoch {:3d} | time: {:5.2f}s | train_total_loss {:5.4f}'.format(
             epoch, time.time() - t0, loss_total / cnt))
         save_model(model, result_file, epoch)
         if (epoch + 1) % args.exponential_decay_step == 0:
-            scheduler.step()
+            if fused is not None:
+                fused.set_lr(fused.lr * args.decay_rate)     # ExponentialLR(gamma=decay_rate).step()
+            else:
+                scheduler.step()
         if (epoch + 1) % args.validate_freq == 0:
             print('------ validate on data: VALIDATE ------')
             metrics = validate(model, valid_loader, args.device, args.norm_method, normalize_statistic,

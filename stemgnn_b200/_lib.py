@@ -8,6 +8,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libstemgnn_b200.so")
 
 MAX_STACK = 2
+ABI_VERSION = 2
 
 
 class Dims(Structure):
@@ -34,7 +35,7 @@ class ModelPtrs(Structure):
 class FwdOpts(Structure):
     _fields_ = [("leaky_alpha", c_float), ("dropout_p", c_float), ("training", c_int),
                 ("dropout_seed", c_uint64), ("dropout_offset", c_uint64), ("dropout_mask", c_void_p),
-                ("gemm_mode", c_int), ("reuse_folded", c_int)]
+                ("gemm_mode", c_int), ("reuse_folded", c_int), ("dropout_offset_dev", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/stemgnn_b200.h declares
@@ -63,6 +64,10 @@ SYMBOLS = {
                                        c_void_p]),
     "stemgnn_eval_metrics": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_void_p, c_void_p]),
+    "stemgnn_mse_loss_grad": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
+    "stemgnn_optimizer_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_float,
+                                       c_float, c_float, c_void_p, c_void_p]),
+    "stemgnn_counters_tick": (c_int, [c_void_p, c_void_p, ctypes.c_ulonglong, c_void_p]),
     "stemgnn_sgemm": (c_int, [c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_float, c_void_p, c_int, c_void_p]),
     "stemgnn_glu_gemm": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
@@ -87,8 +92,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = ABI mismatch, let it propagate
         fn.restype = res
         fn.argtypes = args
-    if lib.stemgnn_version() != 1:
-        raise RuntimeError(f"stemgnn_b200: ABI version {lib.stemgnn_version()} != 1")
+    if lib.stemgnn_version() != ABI_VERSION:
+        raise RuntimeError(f"stemgnn_b200: ABI version {lib.stemgnn_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

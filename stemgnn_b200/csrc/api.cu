@@ -252,6 +252,7 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
   a.key = key; a.query = query; a.qmax = ws.qmax; a.a_raw = ws.a_raw; a.deg = ws.deg;
   a.row_m = ws.row_m; a.row_zinv = ws.row_zinv;
   a.mask = op.dropout_mask; a.seed = op.dropout_seed; a.offset = op.dropout_offset;
+  a.offset_dev = op.dropout_offset_dev;
   a.alpha = op.leaky_alpha; a.p = op.dropout_p;
   a.use_dropout = (op.training && (op.dropout_p > 0.f || op.dropout_mask != nullptr)) ? 1 : 0;
   a.B = B; a.N = N;

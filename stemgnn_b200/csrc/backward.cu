@@ -301,13 +301,15 @@ struct AttnBwdArgs {
   float* d_key;             // (B,N)
   float* d_query;           // (B,N)
   const uint8_t* mask; uint64_t seed, offset;
+  const unsigned long long* offset_dev;
   float alpha, p; int use_dropout; int B, N;
 };
 __device__ __forceinline__ float attn_dp(const AttnBwdArgs& a, int b, int i, int j, float scale) {
   bool keep = true;
   if (a.use_dropout) {
     const uint64_t lin = ((uint64_t)b * a.N + i) * a.N + j;
-    keep = a.mask != nullptr ? (a.mask[lin] != 0) : dropout_keep(a.seed, a.offset, lin, a.p);
+    keep = a.mask != nullptr ? (a.mask[lin] != 0)
+                             : dropout_keep(a.seed, a.offset + (a.offset_dev ? (uint64_t)__ldg(a.offset_dev) : 0ull), lin, a.p);
   }
   return keep ? a.dA[(long long)i * a.N + j] * scale : 0.f;
 }
@@ -667,6 +669,7 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
   ab.key = ws.key; ab.query = ws.query; ab.row_m = ws.row_m; ab.row_zinv = ws.row_zinv; ab.dA = w.dA;
   ab.dots = w.dots; ab.d_key = w.d_key; ab.d_query = w.d_query;
   ab.mask = opts->dropout_mask; ab.seed = opts->dropout_seed; ab.offset = opts->dropout_offset;
+  ab.offset_dev = opts->dropout_offset_dev;
   ab.alpha = opts->leaky_alpha; ab.p = opts->dropout_p;
   ab.use_dropout = (opts->training && (opts->dropout_p > 0.f || opts->dropout_mask != nullptr)) ? 1 : 0;
   ab.B = B; ab.N = N;

@@ -209,7 +209,6 @@ struct GruTcArgs {
   int pipelined;          // 1: MMAs of a K range start as soon as its source CTAs' slices landed
   long long* dbg;         // optional clock64 stamps (STEMGNN_GRU_TC_DBG), null in production
   int dbg_mode;           // 1 both, 2 epilogue stamps only, 3 MMA-warp stamps only
-  int xmode;              // experiment knob (STEMGNN_GRU_TC_X): 1 generic read-back before the MMAs, 2 lo granules first, 3 every lane waits on every barrier
 };
 // stamps are taken under a WARP-UNIFORM condition and the warp is re-converged right after: a lane that diverges in front of
 // elect.sync / tcgen05.ld.sync.aligned breaks those warp-collective instructions (seen as wrong results in early debug builds)
@@ -390,25 +389,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
         const uint32_t par = (uint32_t)((s - 1) >> 1) & 1u;
         const bool dbg_on = ta.dbg != nullptr && ta.dbg_mode != 2 && blockIdx.x == 0 && r == GT_ROUNDS - 1 && s >= dbg_s0 && s < dbg_s0 + 4;
         GT_STAMP(0);
-        if (ta.xmode == 3) {
-          for (int i = 0; i <= last; ++i) mbar_wait_cluster(&hbar[cur * 16 + (q - i + 16 * CS) % CS], par);
-          fence_async_proxy();
-        } else if (lane <= last) {
+        if (lane <= last) {
           mbar_wait_cluster(&hbar[cur * 16 + my_p], par);              // slices of h_{s-1} landed in B[cur]
           fence_async_proxy();         // every observer orders the remote generic-proxy stores before async-proxy reads
         }
         __syncwarp();
-        if (ta.xmode == 1) {           // generic-proxy read-back of the whole tile, then the proxy fence
-          const uint4* bt = reinterpret_cast<const uint4*>(B_sm + (size_t)cur * b_buf);
-          uint32_t acc = 0;
-          for (int i = lane; i < (int)(b_buf / 16); i += 32) {
-            const uint4 v = *reinterpret_cast<const volatile uint4*>(bt + i);
-            acc ^= v.x ^ v.y ^ v.z ^ v.w;
-          }
-          asm volatile("" ::"r"(acc));
-          fence_async_proxy();
-          __syncwarp();
-        }
         GT_STAMP(1);
         if (elect_one()) {
           fence_async_proxy();
@@ -499,9 +484,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       if (idx < n_send) {
         const int slot = idx / n_gran, gr = idx - slot * n_gran;
         const int dest = (q + slot) % CS;
-        int arr = gr / (G * gran_per_b);
-        const int rem = gr - arr * (G * gran_per_b);
-        if (ta.xmode == 2) arr ^= 1;
+        const int arr = gr / (G * gran_per_b), rem = gr - arr * (G * gran_per_b);
         const int bb = rem / gran_per_b, g8 = rem - bb * gran_per_b;
         snd_src[it] = (uint32_t)(((arr * GT_GMAX + bb) * U + 8 * g8) * 2);                  // bytes into stage_sm
         const uint32_t off = sw128_off(arr * 8 + bb, u0 + 8 * g8, B_CHUNK_BYTES);
@@ -713,7 +696,6 @@ int gru_tc_forward(const GruArgs& a, uint8_t* img, int reuse_img, cudaStream_t s
   ta.x_smem = 0;
   static const bool dbg = getenv("STEMGNN_GRU_TC_DBG") != nullptr;
   ta.dbg_mode = dbg ? atoi(getenv("STEMGNN_GRU_TC_DBG")) : 0;
-  ta.xmode = getenv("STEMGNN_GRU_TC_X") ? atoi(getenv("STEMGNN_GRU_TC_X")) : 0;
   static long long* dbg_buf = nullptr;
   if (dbg) {
     if (dbg_buf == nullptr) SG_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));

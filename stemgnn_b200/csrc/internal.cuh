@@ -44,6 +44,7 @@ struct AttnArgs {
   float* row_zinv;       // (B,N) 1 / softmax denominator
   const uint8_t* mask;   // optional explicit keep mask (B,N,N)
   uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device counter added to `offset` (graph replays)
   float alpha, p;
   int use_dropout;       // 0: eval
   int B, N;

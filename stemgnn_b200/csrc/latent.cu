@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) attention_mean_kernel(AttnArgs a) {
   __syncthreads();
   // phase 2: thread per column j: batch mean of the (dropped) probabilities
   const float scale = (a.use_dropout ? 1.0f / (1.0f - a.p) : 1.0f) / (float)B;
+  const uint64_t doff = a.offset + (a.offset_dev != nullptr ? (uint64_t)__ldg(a.offset_dev) : 0ull);
   float dsum = 0.f;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
     float acc = 0.f;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) attention_mean_kernel(AttnArgs a) {
       bool keep = true;
       if (a.use_dropout) {
         const uint64_t lin = ((uint64_t)b * N + i) * N + j;
-        keep = a.mask != nullptr ? (a.mask[lin] != 0) : dropout_keep(a.seed, a.offset, lin, a.p);
+        keep = a.mask != nullptr ? (a.mask[lin] != 0) : dropout_keep(a.seed, doff, lin, a.p);
       }
       if (keep)
         acc += expf(leaky_(s_key[b] + a.query[(long long)b * N + j], a.alpha) - s_m[b]) * s_zinv[b];
