@@ -105,6 +105,8 @@ typedef struct {
   int reuse_folded;         /* 1: the DFT-folded weights already in `workspace` (written by an earlier
                                forward with the SAME parameter values) are reused instead of being
                                recomputed — for inference loops with frozen weights */
+  int graph_mode;           /* 0 = polynomial stack by two N^3 GEMMs (what the reference executes, base_model.py:121-134);
+                               1 = eigendecomposition (fused Laplacian + Jacobi kernel) and U p(Lambda) U^T — eval only */
   const unsigned long long* dropout_offset_dev; /* optional DEVICE counter added to dropout_offset when the kernels run
                                (NULL = none): lets a captured CUDA graph draw a fresh mask on every replay */
 } stemgnn_fwd_opts_t;
@@ -191,6 +193,16 @@ int stemgnn_gather_windows(const float* series, int T, int N, const int32_t* end
 int stemgnn_eval_metrics(const double* forecast_norm, const float* target_norm, long long count, int H, int N,
                          int method, const double* scale, const double* shift, double* partial, int chunks,
                          double* sums, stemgnn_stream_t stream);
+
+/* Fused Laplacian build + symmetric eigendecomposition (north_star; reference hooks base_model.py:106-119 get_laplacian,
+ * :164-165 graph_fft — dead code there, hence opt-in here).  attention_raw (N,N) = batch mean of the softmax attention
+ * BEFORE symmetrisation, degree (N) = its row sums (base_model.py:140-141); the kernel forms
+ * L = D^(diag(deg) - (A + A^T)/2)D^ on the fly and diagonalises it by one-sided Jacobi sweeps held in registers /
+ * distributed shared memory of ONE thread-block cluster.  N <= 512.  With n = N rounded up to even:
+ * eigenvalues (n) and eigenvectors (n,n) row-major, column j <-> eigenvalues[j], UNSORTED; when N is odd one column is
+ * the padding unit vector e_{n-1} with eigenvalue 0.  info[0] = sweeps used, info[1] = 1 if converged (device ints). */
+int stemgnn_laplacian_eig_forward(const float* attention_raw, const float* degree, int N, float* eigenvalues,
+                                  float* eigenvectors, int* info, int max_sweeps, float tol, stemgnn_stream_t stream);
 
 /* ---- train-step tail on the device (reference: models/handler.py:160-166) ------------------------------------------ */
 /* MSELoss(reduction='mean') forward + backward: d_forecast[i] = 2 (forecast[i] - target[i]) / n and

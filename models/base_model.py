@@ -144,6 +144,7 @@ class Model(nn.Module):
         self.leakyrelu = nn.LeakyReLU(self.alpha)
         self.dropout = nn.Dropout(p=dropout_rate)
         self.gemm_mode = runtime.GEMM_AUTO
+        self.graph_mode = "poly"    # "eig": opt-in fused Laplacian + Jacobi eigendecomposition path (eval only)
         self._dropout_calls = 0
         self._philox_ctr = 0       # next free Philox block (dropout masks of successive steps never overlap)
         self._rt = None            # runtime cache (pointer struct, workspaces): never pickled
@@ -163,6 +164,7 @@ class Model(nn.Module):
         d = self.__dict__
         d.setdefault("_rt", None)
         d.setdefault("gemm_mode", runtime.GEMM_AUTO)
+        d.setdefault("graph_mode", "poly")
         d.setdefault("_dropout_calls", 0)
         d.setdefault("_philox_ctr", 0)
         if "dropout_rate" not in d:
@@ -228,12 +230,14 @@ class Model(nn.Module):
         ws = rt["ws"].get(key)
         # the DFT-folded weights inside the workspace stay valid while no parameter was written to
         versions = tuple(p._version for p in rt["params"])
+        graph_mode = 1 if self.graph_mode == "eig" else 0
         reuse = ws is not None and rt.get("folded_for") == (key, versions, self.gemm_mode)
         if ws is None:
             rt["ws"].clear()
             ws = rt["ws"][key] = runtime.alloc_workspace(dims, False, x.device)
         rt["folded_for"] = None
-        opts = runtime.make_opts(self.alpha, 0.0, False, gemm_mode=self.gemm_mode, reuse_folded=reuse)
+        opts = runtime.make_opts(self.alpha, 0.0, False, gemm_mode=self.gemm_mode, reuse_folded=reuse,
+                                 graph_mode=graph_mode)
         out = runtime.model_forward_raw(dims, rt["ptrs"], opts, x, ws, want_mul_L)
         rt["folded_for"] = (key, versions, self.gemm_mode)       # only after a successful call
         return out

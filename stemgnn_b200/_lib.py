@@ -35,7 +35,7 @@ class ModelPtrs(Structure):
 class FwdOpts(Structure):
     _fields_ = [("leaky_alpha", c_float), ("dropout_p", c_float), ("training", c_int),
                 ("dropout_seed", c_uint64), ("dropout_offset", c_uint64), ("dropout_mask", c_void_p),
-                ("gemm_mode", c_int), ("reuse_folded", c_int), ("dropout_offset_dev", c_void_p)]
+                ("gemm_mode", c_int), ("reuse_folded", c_int), ("graph_mode", c_int), ("dropout_offset_dev", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/stemgnn_b200.h declares
@@ -64,6 +64,8 @@ SYMBOLS = {
                                        c_void_p]),
     "stemgnn_eval_metrics": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_void_p, c_void_p]),
+    "stemgnn_laplacian_eig_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                              c_void_p]),
     "stemgnn_mse_loss_grad": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "stemgnn_optimizer_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_float,
                                        c_float, c_float, c_void_p, c_void_p]),

@@ -44,6 +44,10 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
   ws.gru_scratch = take(2 * R);
   ws.gi = take(N * R * 3);
   ws.skbuf = take(8 * (N * N > 3 * N * B * W ? N * N : 3 * N * B * W));
+  ws.eig_lambda = take(N + 2);
+  ws.eig_U = take((N + 2) * (N + 2));
+  ws.eig_S = take((N + 2) * (N + 2));
+  ws.eig_info = reinterpret_cast<int*>(take(4));
   ws.row_m = training ? take(R) : nullptr;
   ws.row_zinv = training ? take(R) : nullptr;
   ws.h_all = training ? take(N * R) : nullptr;
@@ -260,6 +264,12 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
   SG_TRY(launch_attention(a, ws.qmax, st));
   SG_TRY(launch_laplacian(ws.a_raw, ws.deg, attention, ws.mul_L, N, st));
   const size_t nn = (size_t)N * N;
+  if (op.graph_mode == 1 && !op.training && N >= 2 && N <= 512) {
+    // opt-in eigendecomposition path (north_star; the reference's dead `graph_fft` hook): L = U Lambda U^T by the fused
+    // Laplacian + Jacobi kernel, polynomial stack rebuilt as U p(Lambda) U^T
+    SG_TRY(laplacian_eig(ws.a_raw, ws.deg, N, ws.eig_lambda, ws.eig_U, ws.eig_info, 30, 1e-6f, st));
+    return eig_poly_stack(ws.eig_lambda, ws.eig_U, N, ws.eig_S, ws.mul_L, st);
+  }
   // the two N^3 Chebyshev products fill only a few CTAs: deterministic split-K (partials + ordered reduce)
   const int ks = pick_ksplit(N, N, N);
   for (int term = 2; term <= 3; ++term) {

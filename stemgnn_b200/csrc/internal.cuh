@@ -54,6 +54,11 @@ int launch_attention(const AttnArgs& a, float* qmax, cudaStream_t st);
 int launch_laplacian(const float* a_raw, const float* deg, float* attention, float* mul_L, int N,
                      cudaStream_t st);
 
+// ---- fused Laplacian + Jacobi eigensolver (eig.cu), opt-in graph mode ---------------------------------------------------
+int laplacian_eig(const float* a_raw, const float* deg, int N, float* lambda, float* U, int* info, int max_sweeps,
+                  float tol, cudaStream_t st);
+int eig_poly_stack(const float* lambda, const float* U, int N, float* scratch, float* mul_L, cudaStream_t st);
+
 // ---- spectral block helpers (spectral.cu) -----------------------------------------------------------
 struct HeadArgs {
   const float* pre; int ldp;
@@ -123,6 +128,8 @@ struct Workspace {
   float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
   float* skbuf;    // split-K partial products (8 x max(N*N, 3N*B*W) floats)
   float *row_m, *row_zinv, *h_all, *g_r, *g_z, *g_n, *g_hn;
+  float *eig_lambda, *eig_U, *eig_S;   // eig graph mode: eigenvalues (n), eigenvectors (n,n), scaled copy (N,n)
+  int* eig_info;
   BwdWs bwd;
   BlockWs blk[STEMGNN_MAX_STACK];
   size_t floats;

@@ -98,7 +98,7 @@ def alloc_workspace(dims, training, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
-def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AUTO, reuse_folded=False):
+def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AUTO, reuse_folded=False, graph_mode=0):
     o = FwdOpts()
     o.leaky_alpha = float(alpha)
     o.dropout_p = float(p)
@@ -108,6 +108,8 @@ def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AU
     o.dropout_mask = mask.data_ptr() if mask is not None else None
     o.gemm_mode = int(gemm_mode)
     o.reuse_folded = int(bool(reuse_folded))
+    o.graph_mode = int(graph_mode)
+    o.dropout_offset_dev = None
     return o
 
 
