@@ -100,8 +100,9 @@ typedef struct {
   uint64_t dropout_seed;    /* Philox key: the keep-mask of element (b,i,j) is a pure function */
   uint64_t dropout_offset;  /*   of (seed, offset, b, i, j) and is regenerated in backward */
   const uint8_t* dropout_mask; /* optional explicit keep-mask (B,N,N) of {0,1}; overrides Philox */
-  int gemm_mode;            /* 0 = auto (tcgen05 TF32 for the GLU chain when available),
-                               1 = force fp32 FFMA everywhere, 2 = force tcgen05 TF32 */
+  int gemm_mode;            /* 0 = auto: GLU chain on tcgen05 kind::f16 with fp16 hi/lo SPLIT operands (fp32 parity),
+                               1 = force fp32 FFMA everywhere, 2 = round-1 truncated-TF32 tensor-core chain,
+                               3 = bf16 tensor-core operands (BASELINE.json configs[2]; looser, stated tolerance) */
   int reuse_folded;         /* 1: the DFT-folded weights already in `workspace` (written by an earlier
                                forward with the SAME parameter values) are reused instead of being
                                recomputed — for inference loops with frozen weights */

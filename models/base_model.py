@@ -58,9 +58,9 @@ class StockBlockLayer(nn.Module):
         self.backcast_short_cut = nn.Linear(time_step, time_step)
         self.output_channel = 4 * multi_layer
         d = time_step * self.output_channel
-        # stage-level calls (spe_seq_cell / forward of a single block) default to exact fp32 GEMMs;
-        # the fused Model.forward path uses the tcgen05 TF32 GLU chain (Model.gemm_mode)
-        self.gemm_mode = runtime.GEMM_FP32
+        # stage-level calls run the same tensor-core chain as the fused Model.forward path (fp16 hi/lo split operands
+        # keep fp32 parity at the stage boundary); GEMM_FP32 forces the FFMA2 kernels
+        self.gemm_mode = runtime.GEMM_AUTO
         self.GLUs = nn.ModuleList()
         for fan_in in (4 * time_step, d, d):
             self.GLUs.append(GLU(fan_in, d))    # real chain  (even index)
@@ -69,7 +69,7 @@ class StockBlockLayer(nn.Module):
     def __setstate__(self, state):
         # a block unpickled from a REFERENCE-made whole-module checkpoint has no gemm_mode
         self.__dict__.update(state)
-        self.__dict__.setdefault("gemm_mode", runtime.GEMM_FP32)
+        self.__dict__.setdefault("gemm_mode", runtime.GEMM_AUTO)
 
     # -- helpers ---------------------------------------------------------------------------------
     def _block_ptrs(self):

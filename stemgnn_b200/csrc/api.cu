@@ -1,6 +1,7 @@
 // C ABI of stemgnn_b200 (see include/stemgnn_b200.h): workspace carving + forward orchestration.
 // Every kernel is launched on the caller's stream; nothing here allocates device memory.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -74,6 +75,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
       b.save_s[g] = training ? take(R * d) : nullptr;
     }
     b.fs = training ? take(R * T) : nullptr;
+    for (int c = 0; c < 2; ++c) b.hscratch[c] = take((glu_chain_h_scratch_halves((int)R, (int)d, (int)(4 * W)) + 1) / 2);
   }
   if (training) {
     BwdWs& w = ws.bwd;
@@ -160,7 +162,7 @@ int fold_block_weights(const stemgnn_dims_t& dm, const stemgnn_block_params_t& b
 
 // GLU chain on rows G (R x ncol) -> act3 (R x 2d) = [real3 | imag3]
 int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int ncol, int gemm_mode,
-              const BlockWs& b, cudaStream_t st) {
+              const BlockWs& b, cudaStream_t st, int reuse_w = 0) {
   const int R = dm.B * dm.N, T = dm.multi * dm.W, d = 4 * T;
   for (int c = 0; c < 2; ++c) {
     const float* w1l = b.w1f + (size_t)(c * 2 + 0) * d * ncol;
@@ -178,7 +180,14 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
       float* const act[2] = {keep ? a1 : nullptr, keep ? a2 : nullptr};
       float* const sl[3] = {b.save_l[c], b.save_l[2 + c], b.save_l[4 + c]};
       float* const ss[3] = {b.save_s[c], b.save_s[2 + c], b.save_s[4 + c]};
-      const int rc = glu_chain_tc(R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss, st);
+      // default (auto) and bf16 modes: kind::f16 chain — fp16 hi/lo split operands (fp32 parity) or bf16 operands;
+      // gemm_mode 2 keeps the round-1 truncated-TF32 chain
+      int rc = -1;
+      static const bool no_h = getenv("STEMGNN_GLU_NO_F16") != nullptr;
+      if ((gemm_mode == 0 || gemm_mode == 3) && !no_h)
+        rc = glu_chain_h(gemm_mode == 3 ? 1 : 0, R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss,
+                         reinterpret_cast<unsigned short*>(b.hscratch[c]), reuse_w, st);
+      if (rc < 0) rc = glu_chain_tc(R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss, st);
       if (rc == 0) continue;
       if (rc > 0) return rc;
     }
@@ -201,7 +210,7 @@ int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, in
   const int PW = (stack_idx == 0) ? T + W : T;
   if (!reuse_folded) SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
   SG_TRY(launch_gft(mul_L, x_bwn, b.G, skbuf, B, N, W, st));
-  SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st));
+  SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st, reuse_folded));
   {   // pre = [real3 | imag3] @ woutT^T : tcgen05 TF32 unless exact fp32 is requested
     int rc = -1;
     if (gemm_mode != 1)

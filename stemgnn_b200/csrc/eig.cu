@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(1024 / (R > 8 ? 2 : 1), 1) laplacian_eig_kerne
         if (rel > 1e-9f && denom > 1e-30f) {
           const float zeta = (be - al) / (2.f * ga);
           const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          const float c = rsqrtf(1.f + t * t), s = c * t;
+          const float c = 1.0f / sqrtf(1.f + t * t), s = c * t;   // IEEE sqrt / div: rsqrtf's biased error makes the columns' norms drift
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const float g0 = gp[r], g1 = gq[r], v0 = vp[r], v1 = vq[r];
@@ -168,13 +168,19 @@ __global__ void __launch_bounds__(1024 / (R > 8 ? 2 : 1), 1) laplacian_eig_kerne
 
   // ---- store: lambda_j = v_j . g_j (Rayleigh quotient keeps the sign), U[:, j] = v_j ---------------------------------
   if (active) {
-    float lp = 0.f, lq = 0.f;
+    float lp = 0.f, lq = 0.f, np2 = 0.f, nq2 = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       lp = fmaf(vp[r], gp[r], lp);
       lq = fmaf(vq[r], gq[r], lq);
+      np2 = fmaf(vp[r], vp[r], np2);
+      nq2 = fmaf(vq[r], vq[r], nq2);
     }
-    lp = warp_sum(lp); lq = warp_sum(lq);
+    lp = warp_sum(lp); lq = warp_sum(lq); np2 = warp_sum(np2); nq2 = warp_sum(nq2);
+    lp /= np2; lq /= nq2;                              // Rayleigh quotient of the (re-normalised) accumulated rotation
+    const float ip = 1.0f / sqrtf(np2), iq = 1.0f / sqrtf(nq2);
+#pragma unroll
+    for (int r = 0; r < R; ++r) { vp[r] *= ip; vq[r] *= iq; }
     const int jp = 2 * seat, jq = 2 * seat + 1;        // output slots (order is irrelevant: the host side sorts)
     if (lane == 0) { a.lambda[jp] = lp; a.lambda[jq] = lq; }
 #pragma unroll

@@ -94,6 +94,12 @@ int glu_chain_tc(int M, int N, int K1, const float* G, int ldg, const float* con
                  const float* const bias[3][2], float* out3, int ldo3, float* const act[2],
                  float* const save_l[3], float* const save_s[3], cudaStream_t st);
 
+// fused 3-layer GLU chain on tcgen05 kind::f16 (glu_h.cu): mode 0 = fp16 hi/lo split operands (fp32 parity), 1 = bf16
+size_t glu_chain_h_scratch_halves(int M, int N, int K1);
+int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
+                const float* const bias[3][2], float* out3, int ldo3, float* const act[2], float* const save_l[3],
+                float* const save_s[3], unsigned short* scratch, int reuse_w, cudaStream_t st);
+
 // generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
             float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st);
@@ -114,6 +120,7 @@ struct BlockWs {
   float* bc_bwn;   // (B, W, N) backcast, GFT operand layout
   float* save_l[6]; float* save_s[6];   // training: GLU left pre-activation / gate per GLU index
   float* fs;       // training: forecast_source (R, T)
+  float* hscratch[2];   // per chain: 16-bit operand images of the kind::f16 GLU chain (G hi/lo + weight hi/lo)
 };
 // scratch of the backward pass (training workspaces only)
 struct BwdWs {

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import BlockPtrs, Dims, FwdOpts, ModelPtrs
 
-GEMM_AUTO, GEMM_FP32, GEMM_TC = 0, 1, 2
+GEMM_AUTO, GEMM_FP32, GEMM_TC, GEMM_BF16 = 0, 1, 2, 3
 
 # order in which parameters are handed to autograd (names = reference state_dict keys)
 _BLOCK_FIELDS = [("weight", "weight"), ("forecast_w", "forecast.weight"), ("forecast_b", "forecast.bias"),

@@ -38,7 +38,7 @@ def _run(c, mask, gemm_mode, seed_xy=4321):
     return m, xd, forecast, float(loss)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("mode", ["fp32", "tc", "auto"])
 @pytest.mark.parametrize("name", ["grad_multi2", "grad_tiny", "grad_dropmask"])
 def test_backward_vs_reference_gradient_golden(name, mode):
     from stemgnn_b200 import runtime
@@ -48,7 +48,7 @@ def test_backward_vs_reference_gradient_golden(name, mode):
     if c["p_drop"] is not None:
         gen = torch.Generator().manual_seed(99)
         mask = (torch.rand(c["B"], c["N"], c["N"], generator=gen) >= c["p_drop"])
-    m, xd, forecast, loss = _run(c, mask, runtime.GEMM_FP32 if mode == "fp32" else runtime.GEMM_TC)
+    m, xd, forecast, loss = _run(c, mask, {"fp32": runtime.GEMM_FP32, "tc": runtime.GEMM_TC, "auto": runtime.GEMM_AUTO}[mode])
     rtol = 2e-3 if mode == "fp32" else 1e-2
     assert abs(loss - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
     assert_close(forecast, g["forecast"], msg="forecast")

@@ -110,12 +110,12 @@ def _fwd_bwd_vs_cpu(B, N, H, seed, rtol_g, use_reference):
 
 def test_cfg4_global_batch_forward_backward():
     """configs[3] at its global batch on one GPU: (128,325,12,12)."""
-    _fwd_bwd_vs_cpu(128, 325, 12, 41, 2e-3, True)
+    _fwd_bwd_vs_cpu(128, 325, 12, 41, 1e-2, True)    # default mode: weight / input gradient GEMMs on TF32 tensor cores
 
 
 def test_cfg5_n2048_forward_backward():
     """configs[4] node count: (8,2048,12,3) — the GRU runs beyond the single-cluster envelope."""
-    _fwd_bwd_vs_cpu(8, 2048, 3, 43, 2e-3, False)
+    _fwd_bwd_vs_cpu(8, 2048, 3, 43, 1e-2, False)
 
 
 def test_cfg3_bf16_mode():

