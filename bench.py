@@ -366,7 +366,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": roof,
             "roofline_glu": None if not glu_ms else {
-                "kernel": "glu_chain_tc_kernel (tcgen05, the 3 GLU layers of one chain over B*N rows, one launch)",
+                "kernel": "glu_chain_h_kernel<SPLIT> (tcgen05 kind::f16, fp16 hi/lo split operands: 3 MMAs per product; the 3 GLU "
+                          "layers of one chain over B*N rows) + its operand-split pre-pass (7 small launches: G and 6 weights)",
                 "bound": "tensor", "achieved": glu_flops / (glu_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": glu_flops / (glu_ms * 1e-3) / 1e12 / peak_tf, "ms_per_launch": glu_ms,
                 "algorithmic_flops_per_launch": glu_flops, "peak_source": peak_src,
@@ -403,9 +404,10 @@ def time_glu_chain(lib, dev, B, N, W, flush):
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     wp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in ws])
     bp = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bs])
+    scratch = torch.empty(int(lib.stemgnn_glu_chain_scratch_bytes(R, d, K1)), dtype=torch.uint8, device=dev)
 
     def call():
-        rc = lib.stemgnn_glu_chain(R, d, K1, G.data_ptr(), K1, wp, bp, out.data_ptr(), d, 0, st)
+        rc = lib.stemgnn_glu_chain(R, d, K1, G.data_ptr(), K1, wp, bp, out.data_ptr(), d, 0, scratch.data_ptr(), st)
         if rc:
             raise RuntimeError(lib.stemgnn_last_error().decode())
     for _ in range(3):
@@ -417,7 +419,7 @@ def time_glu_chain(lib, dev, B, N, W, flush):
         e0.record(); call(); e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
-    flops = 2.0 * R * 2 * d * (K1 + d + d)
+    flops = 2.0 * R * 2 * d * (K1 + d + d)          # algorithmic: one product per element pair (the split issues 3)
     return tot / reps, flops
 
 

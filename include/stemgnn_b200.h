@@ -205,6 +205,15 @@ int stemgnn_eval_metrics(const double* forecast_norm, const float* target_norm, 
 int stemgnn_laplacian_eig_forward(const float* attention_raw, const float* degree, int N, float* eigenvalues,
                                   float* eigenvectors, int* info, int max_sweeps, float tol, stemgnn_stream_t stream);
 
+/* The three GLU layers of one chain (base_model.py:52-54) as ONE fused tensor-core launch (measurement / test hook of the
+ * kernel the model path runs).  G (M,K1) lda ldg; weights[6] = {W1_left, W1_right, W2_left, W2_right, W3_left, W3_right}
+ * ((N,K1) for layer 1, (N,N) else), biases[6] likewise (N); out3 (M,N) ldo3.  mode: 0 = fp16 hi/lo split operands,
+ * 2 = truncated TF32 (round-1 kernel), 3 = bf16.  scratch: stemgnn_glu_chain_scratch_bytes() bytes of device memory. */
+int stemgnn_glu_chain(int M, int N, int K1, const float* G, int ldg, const float* const* weights,
+                      const float* const* biases, float* out3, int ldo3, int mode, void* scratch,
+                      stemgnn_stream_t stream);
+size_t stemgnn_glu_chain_scratch_bytes(int M, int N, int K1);
+
 /* ---- train-step tail on the device (reference: models/handler.py:160-166) ------------------------------------------ */
 /* MSELoss(reduction='mean') forward + backward: d_forecast[i] = 2 (forecast[i] - target[i]) / n and
  * loss_accum[0] += mean((forecast - target)^2) (device scalar: no per-step host sync, handler.py:166). */

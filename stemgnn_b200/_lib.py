@@ -66,6 +66,9 @@ SYMBOLS = {
                                      c_void_p, c_int, c_void_p, c_void_p]),
     "stemgnn_laplacian_eig_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                               c_void_p]),
+    "stemgnn_glu_chain": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                  c_void_p]),
+    "stemgnn_glu_chain_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "stemgnn_mse_loss_grad": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "stemgnn_optimizer_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_float,
                                        c_float, c_float, c_void_p, c_void_p]),

@@ -504,6 +504,25 @@ int stemgnn_glu_gemm(int M, int N, int K, const float* A, int lda, const float* 
   return glu_layer(M, N, K, A, lda, Wl, bl, Wr, br, out, ldo, nullptr, nullptr, use_tc ? 2 : 1, st);
 }
 
+int stemgnn_glu_chain(int M, int N, int K1, const float* G, int ldg, const float* const* weights, const float* const* biases,
+                      float* out3, int ldo3, int mode, void* scratch, stemgnn_stream_t stream) {
+  clear_error();
+  SG_CHECK(M > 0 && G && weights && biases && out3 && scratch, "glu_chain: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* const w[3][2] = {{weights[0], weights[1]}, {weights[2], weights[3]}, {weights[4], weights[5]}};
+  const float* const b[3][2] = {{biases[0], biases[1]}, {biases[2], biases[3]}, {biases[4], biases[5]}};
+  float* const act[2] = {nullptr, nullptr};
+  float* const sv[3] = {nullptr, nullptr, nullptr};
+  int rc;
+  if (mode == 2) rc = glu_chain_tc(M, N, K1, G, ldg, w, b, out3, ldo3, act, sv, sv, st);
+  else rc = glu_chain_h(mode == 3 ? 1 : 0, M, N, K1, G, ldg, w, b, out3, ldo3, act, sv, sv,
+                        static_cast<unsigned short*>(scratch), 0, st);
+  SG_CHECK(rc >= 0, "glu_chain: unsupported shape M=%d N=%d K1=%d", M, N, K1);
+  return rc;
+}
+
+size_t stemgnn_glu_chain_scratch_bytes(int M, int N, int K1) { return glu_chain_h_scratch_halves(M, N, K1) * 2; }
+
 int stemgnn_model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* params,
                            const stemgnn_fwd_opts_t* opts, const float* x, const float* d_forecast,
                            const float* d_attention, const stemgnn_grads_t* grads, float* d_x,

@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
         const bool dbg_on = ta.dbg != nullptr && ta.dbg_mode != 2 && blockIdx.x == 0 && r == GT_ROUNDS - 1 && s >= dbg_s0 && s < dbg_s0 + 4;
         GT_STAMP(0);
         if (lane <= last) {
-          mbar_wait_cluster(&hbar[cur * 16 + my_p], par);              // slices of h_{s-1} landed in B[cur]
+          // plain (cta-scope) acquire: the cluster-scope form makes ptxas add CCTL.IVALL (an L1 invalidate, 8 % of the
+          // kernel's stall samples in profiles/r02_ncu_gru_tc_stalls.txt) although the payload lives in shared memory
+          mbar_wait(&hbar[cur * 16 + my_p], par);                      // slices of h_{s-1} landed in B[cur]
           fence_async_proxy();         // every observer orders the remote generic-proxy stores before async-proxy reads
         }
         __syncwarp();
