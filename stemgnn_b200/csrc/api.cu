@@ -186,7 +186,8 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
       static const bool no_h = getenv("STEMGNN_GLU_NO_F16") != nullptr;
       if ((gemm_mode == 0 || gemm_mode == 3) && !no_h)
         rc = glu_chain_h(gemm_mode == 3 ? 1 : 0, R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss,
-                         reinterpret_cast<unsigned short*>(b.hscratch[c]), reuse_w, st);
+                         reinterpret_cast<unsigned short*>(b.hscratch[c]), reuse_w,
+                         c == 1 ? reinterpret_cast<const unsigned short*>(b.hscratch[0]) : nullptr, st);
       if (rc < 0) rc = glu_chain_tc(R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss, st);
       if (rc == 0) continue;
       if (rc > 0) return rc;
@@ -516,7 +517,7 @@ int stemgnn_glu_chain(int M, int N, int K1, const float* G, int ldg, const float
   int rc;
   if (mode == 2) rc = glu_chain_tc(M, N, K1, G, ldg, w, b, out3, ldo3, act, sv, sv, st);
   else rc = glu_chain_h(mode == 3 ? 1 : 0, M, N, K1, G, ldg, w, b, out3, ldo3, act, sv, sv,
-                        static_cast<unsigned short*>(scratch), 0, st);
+                        static_cast<unsigned short*>(scratch), 0, nullptr, st);
   SG_CHECK(rc >= 0, "glu_chain: unsupported shape M=%d N=%d K1=%d", M, N, K1);
   return rc;
 }

@@ -392,10 +392,13 @@ size_t glu_chain_h_scratch_halves(int M, int N, int K1) {
 }
 
 // mode: 0 = SPLIT (fp16 hi/lo, fp32 parity), 1 = BF16.  scratch: glu_chain_h_scratch_halves() 16-bit elements, 16-byte aligned.
-// reuse_w: the weight images in `scratch` are still valid (frozen parameters).  Returns -1 when unsupported.
+// reuse_w: the weight images in `scratch` are still valid (frozen parameters).  g_shared: when non-null, the 16-bit images of G
+// live at the START of that other scratch buffer (the real and imag chains of a block read the same rows) and are already
+// converted.  Returns -1 when unsupported.
 int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
                 const float* const bias[3][2], float* out3, int ldo3, float* const act[2], float* const save_l[3],
-                float* const save_s[3], unsigned short* scratch, int reuse_w, cudaStream_t st) {
+                float* const save_s[3], unsigned short* scratch, int reuse_w, const unsigned short* g_shared,
+                cudaStream_t st) {
   if (N % 16 != 0 || N < 16 || N > 256 || K1 < 1 || K1 > 256 || (ldo3 & 3) != 0 || scratch == nullptr) return -1;
   if ((reinterpret_cast<uintptr_t>(scratch) & 15) || (reinterpret_cast<uintptr_t>(out3) & 15)) return -1;
   EncodeFn enc = encode_fn();
@@ -403,9 +406,9 @@ int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const f
   const bool split = mode == 0;
   const int k1p = (K1 + 63) / 64 * 64;
   // scratch layout (16-bit elements): G_hi, G_lo (M x k1p) | per layer, side: W_hi, W_lo (N x Kp)
-  unsigned short* g_hi = scratch;
+  unsigned short* g_hi = g_shared != nullptr ? const_cast<unsigned short*>(g_shared) : scratch;
   unsigned short* g_lo = g_hi + (size_t)M * k1p;
-  unsigned short* wp = g_lo + (size_t)M * k1p;
+  unsigned short* wp = scratch + 2 * (size_t)M * k1p;
   unsigned short* w_img[3][2][2];
   int kp[3] = {k1p, N, N};
   for (int l = 0; l < 3; ++l)
@@ -422,7 +425,7 @@ int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const f
     SG_LAUNCH_CHECK("split_rows_kernel");
     return 0;
   };
-  SG_TRY(conv(G, M, K1, ldg, g_hi, g_lo, k1p));
+  if (g_shared == nullptr) SG_TRY(conv(G, M, K1, ldg, g_hi, g_lo, k1p));
   if (!reuse_w)
     for (int l = 0; l < 3; ++l)
       for (int sd = 0; sd < 2; ++sd)

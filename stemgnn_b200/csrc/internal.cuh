@@ -98,7 +98,8 @@ int glu_chain_tc(int M, int N, int K1, const float* G, int ldg, const float* con
 size_t glu_chain_h_scratch_halves(int M, int N, int K1);
 int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
                 const float* const bias[3][2], float* out3, int ldo3, float* const act[2], float* const save_l[3],
-                float* const save_s[3], unsigned short* scratch, int reuse_w, cudaStream_t st);
+                float* const save_s[3], unsigned short* scratch, int reuse_w, const unsigned short* g_shared,
+                cudaStream_t st);
 
 // generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
