@@ -298,6 +298,7 @@ def run_ours(args, rank, world, local_rank):
             f, _a = model(x_host.to(dev, non_blocking=True))
             out_host.copy_(f, non_blocking=True)
         barrier()
+        sys.stderr.write(f"[bench] before e2e: graph captures {(model._rt or {}).get('captures')}\n")
         t0 = time.perf_counter()
         for _ in range(steps):
             xd = x_host.to(dev, non_blocking=True)                      # H2D of the step's input
@@ -306,6 +307,8 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         barrier()
+        sys.stderr.write(f"[bench] e2e {e2e_s / steps * 1e3:.3f} ms/step; graph captures so far: "
+                         f"{(model._rt or {}).get('captures')}, use_cuda_graph={model.use_cuda_graph}\n")
 
     # ---- second column: training step (handler.py:160-165) ----------------------------------------------
     train = None

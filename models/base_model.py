@@ -253,6 +253,7 @@ class Model(nn.Module):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         f_s, a_s, _ = runtime.model_forward_raw(dims, rt["ptrs"], opts, xs, ws, False)
+                    rt["captures"] = rt.get("captures", 0) + 1
                     cg = rt["cuda_graph"] = {"sig": sig, "graph": g, "x": xs, "forecast": f_s, "attention": a_s, "opts": opts}
                 except Exception:                       # capture unsupported here: stay on the eager launch path
                     self.use_cuda_graph = False

@@ -1073,6 +1073,12 @@ int gru_keyquery_forward(const GruArgs& a_in, int path, float* scratch, cudaStre
     const int rc = gru_tc_forward(a, reinterpret_cast<uint8_t*>(a.gi), a.tc_reuse, st);
     if (rc == 0) return 0;
     if (rc > 0) return rc;
+    if (a.N > 512) {      // beyond every cluster kernel: one tensor-core launch per step, W_hh streamed from L2
+      const int rc2 = gru_step_tc_forward(a, reinterpret_cast<uint8_t*>(a.gi), (size_t)3 * a.N * a.N * a.B * sizeof(float),
+                                          a.tc_reuse, st);
+      if (rc2 == 0) return 0;
+      if (rc2 > 0) return rc2;
+    }
     SG_CHECK(path != 3, "gru: tensor-core path unavailable for N=%d W=%d on this device", a.N, a.W);
   }
   SG_TRY(gru_input_proj(a, st));

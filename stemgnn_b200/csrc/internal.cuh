@@ -26,6 +26,9 @@ struct GruArgs {
 int gru_tc_forward(const GruArgs& a, uint8_t* img, int reuse_img, cudaStream_t st);
 size_t gru_tc_image_bytes(int N, int W);
 const char* gru_tc_kernel_name();
+// per-step tensor-core path for N beyond the cluster envelope (gru_step_tc.cu): W_hh images streamed from L2 by TMA
+size_t gru_step_tc_scratch_bytes(int B, int N);
+int gru_step_tc_forward(const GruArgs& a, uint8_t* scratch, size_t scratch_bytes, int reuse_img, cudaStream_t st);
 int gru_keyquery_forward(const GruArgs& a, int path, float* scratch, cudaStream_t st);
 // persistent-cluster BPTT (one launch); -1 = unsupported here, use the per-step kernels
 int gru_bwd_cluster(const float* w_hh, const float* wk, const float* wq, const float* d_key,
