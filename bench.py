@@ -329,7 +329,21 @@ def run_ours(args, rank, world, local_rank):
     peak_tf, peak_gbs, peak_src, extra_peaks = _peaks()
     gru_flops = 6.0 * B * N ** 3 + 12.0 * B * N * N               # recurrence + gates
     roof = None
-    if gru_ms:
+    if gru_ms and N > 512:
+        # cfg5 envelope: W_hh does not fit on chip; every step streams its fp16 hi/lo images (2 x 3N x N x 2 bytes) plus the
+        # h tile of every CTA from L2/HBM -> the recurrence is bandwidth-bound (gru_step_tc.cu)
+        nt, kp = (N + 39) // 40, (N + 63) // 64 * 64
+        step_bytes = 2.0 * nt * 128 * kp * 2 + nt * ((B + 31) // 32) * 64 * kp * 2
+        ach = step_bytes * N / (gru_ms * 1e-3) / 1e9
+        roof = {"kernel": "gru_step_tc_kernel x N launches (tcgen05 kind::f16, W_hh hi/lo images streamed by TMA)",
+                "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
+                "peak_source": peak_src + " (copy bandwidth; the 50 MB image set is L2-resident, so this is a lower bound "
+                                          "on the applicable peak)",
+                "ms_per_launch": gru_ms / N, "launches": N, "share_of_step": gru_ms / (dev_ms / steps),
+                "algorithmic_bytes_per_launch": step_bytes, "algorithmic_flops_per_forward": gru_flops,
+                "measured_other_peaks": extra_peaks,
+                "note": f"{N} dependent steps, one launch each; bytes = W_hh hi/lo images + per-CTA h tiles per step"}
+    elif gru_ms:
         ach = gru_flops / (gru_ms * 1e-3) / 1e12
         traffic = None
         try:
@@ -345,7 +359,8 @@ def run_ours(args, rank, world, local_rank):
                 if traffic else None,
                 "peak_source": peak_src, "ms_per_launch": gru_ms, "share_of_step": gru_ms / (dev_ms / steps),
                 "algorithmic_flops_per_launch": gru_flops, "measured_other_peaks": extra_peaks,
-                "note": f"recurrence of {N} dependent steps; flops = 6BN^3 + 12BN^2 (SURVEY.md §8(d))"}
+                "note": f"recurrence of {N} dependent steps (latency chain: exchange -> 2*ceil(N/16) MMAs -> gates per step); "
+                        "flops = 6BN^3 + 12BN^2 counted once (SURVEY.md §8(d)), the split-operand kernel issues 4x of them"}
 
     # ---- parity: "MAE vs ref" on the SAME inputs / weights, reference CPU forward timed beside it ----------------
     ref, x_ref, cpu_ms, cpu_steps, threads = cpu_reference(args.config)

@@ -162,7 +162,7 @@ int fold_block_weights(const stemgnn_dims_t& dm, const stemgnn_block_params_t& b
 
 // GLU chain on rows G (R x ncol) -> act3 (R x 2d) = [real3 | imag3]
 int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int ncol, int gemm_mode,
-              const BlockWs& b, cudaStream_t st, int reuse_w = 0) {
+              const BlockWs& b, cudaStream_t st, int reuse_w = 0, int g_ready = 0) {
   const int R = dm.B * dm.N, T = dm.multi * dm.W, d = 4 * T;
   for (int c = 0; c < 2; ++c) {
     const float* w1l = b.w1f + (size_t)(c * 2 + 0) * d * ncol;
@@ -187,7 +187,7 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
       if ((gemm_mode == 0 || gemm_mode == 3) && !no_h)
         rc = glu_chain_h(gemm_mode == 3 ? 1 : 0, R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss,
                          reinterpret_cast<unsigned short*>(b.hscratch[c]), reuse_w,
-                         c == 1 ? reinterpret_cast<const unsigned short*>(b.hscratch[0]) : nullptr, st);
+                         c == 1 ? reinterpret_cast<const unsigned short*>(b.hscratch[0]) : nullptr, st, g_ready);
       if (rc < 0) rc = glu_chain_tc(R, d, ncol, b.G, ncol, w, bias, b.act3 + (size_t)c * d, 2 * d, act, sl, ss, st);
       if (rc == 0) continue;
       if (rc > 0) return rc;
@@ -210,8 +210,14 @@ int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, in
   const int B = dm.B, N = dm.N, W = dm.W, T = dm.multi * W, d = 4 * T, R = B * N;
   const int PW = (stack_idx == 0) ? T + W : T;
   if (!reuse_folded) SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
-  SG_TRY(launch_gft(mul_L, x_bwn, b.G, skbuf, B, N, W, st));
-  SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st, reuse_folded));
+  // the split-K reduction of the graph-Fourier GEMM also emits the 16-bit operand images of G for the kind::f16 chain
+  int g_ready = 0;
+  static const bool no_h = getenv("STEMGNN_GLU_NO_F16") != nullptr;
+  const bool h_chain = (gemm_mode == 0 || gemm_mode == 3) && !no_h && d % 16 == 0 && d <= 256 && 3 * W <= 256;
+  SG_TRY(launch_gft(mul_L, x_bwn, b.G, skbuf, B, N, W, st,
+                    h_chain ? reinterpret_cast<unsigned short*>(b.hscratch[0]) : nullptr, (3 * W + 63) / 64 * 64,
+                    gemm_mode == 3 ? 1 : 0, &g_ready));
+  SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st, reuse_folded, g_ready));
   {   // pre = [real3 | imag3] @ woutT^T : tcgen05 TF32 unless exact fp32 is requested
     int rc = -1;
     if (gemm_mode != 1)

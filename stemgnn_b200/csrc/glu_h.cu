@@ -398,7 +398,7 @@ size_t glu_chain_h_scratch_halves(int M, int N, int K1) {
 int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
                 const float* const bias[3][2], float* out3, int ldo3, float* const act[2], float* const save_l[3],
                 float* const save_s[3], unsigned short* scratch, int reuse_w, const unsigned short* g_shared,
-                cudaStream_t st) {
+                cudaStream_t st, int g_ready) {
   if (N % 16 != 0 || N < 16 || N > 256 || K1 < 1 || K1 > 256 || (ldo3 & 3) != 0 || scratch == nullptr) return -1;
   if ((reinterpret_cast<uintptr_t>(scratch) & 15) || (reinterpret_cast<uintptr_t>(out3) & 15)) return -1;
   EncodeFn enc = encode_fn();
@@ -425,7 +425,7 @@ int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const f
     SG_LAUNCH_CHECK("split_rows_kernel");
     return 0;
   };
-  if (g_shared == nullptr) SG_TRY(conv(G, M, K1, ldg, g_hi, g_lo, k1p));
+  if (g_shared == nullptr && !g_ready) SG_TRY(conv(G, M, K1, ldg, g_hi, g_lo, k1p));   // g_ready: written by the GFT reduce
   if (!reuse_w)
     for (int l = 0; l < 3; ++l)
       for (int sd = 0; sd < 2; ++sd)

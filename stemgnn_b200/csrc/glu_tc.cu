@@ -642,8 +642,7 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   // CTA pairs with multicast weights unless disabled (STEMGNN_GLU_NO_MULTICAST) or N/2 breaks the 8-row atom
   static const bool no_mc = getenv("STEMGNN_GLU_NO_MULTICAST") != nullptr;
   const int csz = (!no_mc && (N % 16 == 0)) ? 2 : 1;
-  static const bool bk16 = getenv("STEMGNN_GLU_BK16") != nullptr;
-  const int bk = bk16 ? 16 : 32;
+  const int bk = 32;      // (the 64-byte-row / 5-stage variant of round 1 measured no gain and was removed)
   const int nstage = bk == 32 ? 2 : 5;
   CUtensorMap ma, ml, mr;
   if (!make_map(enc, &ma, A, M, K, lda, TC_BM, bk) || !make_map(enc, &ml, Wl, N, K, K, N / csz, bk) ||
@@ -656,15 +655,12 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   if (smem > smem_set) {
     SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   GluTcArgs g = {bl, br, out, ldo, save_l, save_s, lds, M, N, K};
   const int tiles = ceil_div(M, TC_BM);
   if (csz == 1) {
-    if (bk == 32) glu_tc_kernel<1, 32><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
-    else glu_tc_kernel<1, 16><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
+    glu_tc_kernel<1, 32><<<tiles, TC_THREADS, smem, st>>>(ma, ml, mr, g);
     SG_LAUNCH_CHECK("glu_tc_kernel");
     return 0;
   }
@@ -680,8 +676,7 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (bk == 32) SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2, 32>, ma, ml, mr, g));
-  else SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2, 16>, ma, ml, mr, g));
+  SG_CUDA(cudaLaunchKernelEx(&cfg, glu_tc_kernel<2, 32>, ma, ml, mr, g));
   count_launch();
   return 0;
 }

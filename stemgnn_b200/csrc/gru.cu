@@ -18,8 +18,7 @@
 //   * BPTT (gru_bwd_cluster_kernel) reuses the layout: local gate gradients, partial W_hh^T d_gh over
 //     the resident rows, reduce-scatter of the partial sums over DSMEM.
 // A generic per-step-launch path covers N > 512 or devices that refuse the 16-CTA cluster.
-// Variants kept for measurement (opt-in through STEMGNN_GRU_MODE / STEMGNN_GRU_UW): two software-
-// pipelined groups per cluster, unit-wise step; both measured slower (profiles/README.md).
+// Since round 2 this file is the FALLBACK of the tensor-core recurrence (gru_tc.cu, gru_step_tc.cu) and the home of the BPTT.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -366,274 +365,6 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(GruArgs a) 
       a.query[(long long)(b0 + g * G + fb) * N + u] = query_acc[g];
     }
   }
-}
-
-// -------------------------------------------------------------------------------------------------
-// Unit-wise variant of the step (one group of G sequences): the warp's UPW hidden units are processed one
-// after the other — mat-vec of the unit's 3 rows, register-only reduce-scatter, gate math on lanes 0..G-1 —
-// inside one fully unrolled region without barriers, so the shuffle / transcendental latency of unit i
-// overlaps the FFMA2 stream of unit i+1 (the monolithic version exposes ~900 cycles of reduce + gates).
-template <int JC, int UPW, int CS, int G>
-__global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_uw_kernel(GruArgs a) {
-  constexpr int KP = 128 * JC;
-  constexpr int ULOC = GRU_WARPS * UPW;
-  constexpr int ROWS = 3 * UPW;
-  static_assert(G <= 8, "slot layout");
-
-  extern __shared__ __align__(16) float smem[];
-  float* Wsm = smem;                              // [3*ULOC][KP]
-  float* hbuf = Wsm + 3 * ULOC * KP;              // [2][G][KP]
-  float* stage = hbuf + 2 * G * KP;               // [5][G][32]
-  uint64_t* hbar = reinterpret_cast<uint64_t*>(stage + 5 * G * 32);   // [2]
-
-  cg::cluster_group cluster = cg::this_cluster();
-  const int q = (int)cluster.block_rank();
-  const int cid = blockIdx.x / CS;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int N = a.N, B = a.B;
-  const int U = (N + CS - 1) / CS;
-  const int UP = (U + 3) & ~3;
-  const int UP4 = UP >> 2;
-  const int u0 = q * U;
-  const int b0 = cid * G;
-
-  for (int idx = tid; idx < 3 * ULOC * KP; idx += GRU_THREADS) {
-    const int row = idx / KP, kp = idx - row * KP;
-    const int lu = row / 3, gate = row - lu * 3;
-    const int u = u0 + lu;
-    const int src_cta = kp / UP, src_lu = kp - src_cta * UP;
-    const int k = src_cta * U + src_lu;
-    float v = 0.f;
-    if (lu < U && u < N && src_cta < CS && src_lu < U && k < N)
-      v = __ldg(a.w_hh + ((long long)gate * N + u) * N + k);
-    Wsm[idx] = v;
-  }
-  for (int idx = tid; idx < 2 * G * KP; idx += GRU_THREADS) hbuf[idx] = 0.f;
-  for (int idx = tid; idx < 5 * G * 32; idx += GRU_THREADS) stage[idx] = 0.f;
-  if (tid == 0) {
-    mbar_init_(&hbar[0], 1);
-    mbar_init_(&hbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  const uint32_t tx_bytes = (uint32_t)(CS * G * UP * sizeof(float));
-
-  constexpr int SEND_ITEMS = (CS * G * 8 + GRU_THREADS - 1) / GRU_THREADS;
-  int snd_src[SEND_ITEMS];
-  uint32_t snd_dst[SEND_ITEMS], snd_bar[SEND_ITEMS];
-#pragma unroll
-  for (int it = 0; it < SEND_ITEMS; ++it) {
-    const int idx = tid + it * GRU_THREADS;
-    snd_src[it] = -1;
-    snd_dst[it] = snd_bar[it] = 0;
-    if (idx < CS * G * UP4) {
-      const int dest = idx / (G * UP4);
-      const int rem = idx - dest * (G * UP4);
-      const int bb = rem / UP4, i4 = rem - bb * UP4;
-      snd_src[it] = bb * 32 + 4 * i4;
-      snd_dst[it] = map_to_cta(smem_addr_u32(hbuf + bb * KP + q * UP + 4 * i4), (uint32_t)dest);
-      snd_bar[it] = map_to_cta(smem_addr_u32(&hbar[0]), (uint32_t)dest);
-    }
-  }
-
-  // lanes 0..G-1 finalise sequence fb = lane of every unit of this warp
-  const int fb = lane;
-  const bool flane = lane < G;
-  const bool bvalid = flane && (b0 + fb) < B;
-  bool fin[UPW];
-  float bhr[UPW], bhz[UPW], bhn[UPW], key_acc[UPW], query_acc[UPW], gi_r[UPW], gi_z[UPW], gi_n[UPW];
-  auto load_gi = [&](int s, int i, float& gr, float& gz, float& gn) {
-    gr = gz = gn = 0.f;
-    if (fin[i] && bvalid) {
-      const float* g = a.gi + ((long long)s * B + (b0 + fb)) * (3 * N) + u0 + w * UPW + i;
-      gr = __ldg(g);
-      gz = __ldg(g + N);
-      gn = __ldg(g + 2 * N);
-    }
-  };
-#pragma unroll
-  for (int i = 0; i < UPW; ++i) {
-    const int lu = w * UPW + i, u = u0 + lu;
-    fin[i] = flane && (lu < U) && (u < N);
-    bhr[i] = bhz[i] = bhn[i] = 0.f;
-    if (fin[i]) {
-      bhr[i] = __ldg(a.b_hh + u);
-      bhz[i] = __ldg(a.b_hh + N + u);
-      bhn[i] = __ldg(a.b_hh + 2 * N + u);
-    }
-    key_acc[i] = query_acc[i] = 0.f;
-    load_gi(0, i, gi_r[i], gi_z[i], gi_n[i]);
-  }
-  float wk_s = __ldg(a.wk + 0), wq_s = __ldg(a.wq + 0);
-
-  __syncthreads();
-  cluster.sync();
-
-  for (int s = 0; s < N; ++s) {
-    const int cur = s & 1, nxt = cur ^ 1;
-    if (tid == 0 && s + 1 < N) mbar_expect_tx_(&hbar[nxt], tx_bytes);
-    if (s > 0) mbar_wait_cluster_(&hbar[cur], (uint32_t)((s - 1) >> 1) & 1u);
-    float nx_wk = 0.f, nx_wq = 0.f;
-    if (s + 1 < N) {
-      nx_wk = __ldg(a.wk + s + 1);
-      nx_wq = __ldg(a.wq + s + 1);
-    }
-    const float* hb_cur = hbuf + cur * G * KP;
-    float4 h[G][JC];
-#pragma unroll
-    for (int bb = 0; bb < G; ++bb)
-#pragma unroll
-      for (int j = 0; j < JC; ++j)
-        h[bb][j] = *reinterpret_cast<const float4*>(hb_cur + bb * KP + 128 * j + 4 * lane);
-
-#pragma unroll
-    for (int i = 0; i < UPW; ++i) {
-      const int lu = w * UPW + i;
-      float nr = 0.f, nz = 0.f, nn = 0.f;
-      if (s + 1 < N) load_gi(s + 1, i, nr, nz, nn);
-      // mat-vec of the unit's r, z, n rows
-      float2 acc[3][G];
-      const float* wbase = Wsm + (long long)(w * ROWS + 3 * i) * KP + 4 * lane;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int bb = 0; bb < G; ++bb) acc[r][bb] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < JC; ++j) {
-          const float4 wv = *reinterpret_cast<const float4*>(wbase + r * KP + 128 * j);
-#pragma unroll
-          for (int bb = 0; bb < G; ++bb) {
-            acc[r][bb] = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(h[bb][j].x, h[bb][j].y), acc[r][bb]);
-            acc[r][bb] = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(h[bb][j].z, h[bb][j].w), acc[r][bb]);
-          }
-        }
-      }
-      // register-only reduction: slots gate*8 + b; gates r,z form a 16-chunk, gate n an 8-chunk
-      float c16[16], c8[8];
-#pragma unroll
-      for (int bb = 0; bb < 8; ++bb) {
-        c16[bb] = bb < G ? acc[0][bb < G ? bb : 0].x + acc[0][bb < G ? bb : 0].y : 0.f;
-        c16[8 + bb] = bb < G ? acc[1][bb < G ? bb : 0].x + acc[1][bb < G ? bb : 0].y : 0.f;
-        c8[bb] = bb < G ? acc[2][bb < G ? bb : 0].x + acc[2][bb < G ? bb : 0].y : 0.f;
-      }
-      const float t16 = warp_reduce_scatter<16>(c16, lane);     // lane l: total of slot l / 2
-      const float t8 = warp_reduce_scatter<8>(c8, lane);        // lane l: total of slot 16 + l / 4
-      const float gh_r = __shfl_sync(0xffffffffu, t16, (2 * fb) & 31);
-      const float gh_z = __shfl_sync(0xffffffffu, t16, (2 * (8 + fb)) & 31);
-      const float gh_n = __shfl_sync(0xffffffffu, t8, (4 * fb) & 31);
-      if (flane) {
-        float hn = 0.f;
-        if (fin[i]) {
-          const float hprev = hb_cur[fb * KP + q * UP + lu];
-          const float r = fast_sigmoid(gi_r[i] + gh_r + bhr[i]);
-          const float zt = fast_sigmoid(gi_z[i] + gh_z + bhz[i]);
-          const float nt = fast_tanh(gi_n[i] + r * (gh_n + bhn[i]));
-          hn = (1.f - zt) * nt + zt * hprev;
-          key_acc[i] = fmaf(hn, wk_s, key_acc[i]);
-          query_acc[i] = fmaf(hn, wq_s, query_acc[i]);
-          if (a.g_r != nullptr) {
-            stage[(1 * G + fb) * 32 + lu] = r;
-            stage[(2 * G + fb) * 32 + lu] = zt;
-            stage[(3 * G + fb) * 32 + lu] = nt;
-            stage[(4 * G + fb) * 32 + lu] = gh_n + bhn[i];
-          }
-        }
-        stage[fb * 32 + lu] = hn;
-      }
-      gi_r[i] = nr; gi_z[i] = nz; gi_n[i] = nn;
-    }
-    __syncthreads();
-    if (s + 1 < N) {
-      const uint32_t dst_off = (uint32_t)(nxt * G * KP * 4);
-      const uint32_t bar_off = (uint32_t)(nxt * 8);
-#pragma unroll
-      for (int it = 0; it < SEND_ITEMS; ++it) {
-        if (snd_src[it] >= 0) {
-          const float4 v = *reinterpret_cast<const float4*>(stage + snd_src[it]);
-          st_async_v4(snd_dst[it] + dst_off, v, snd_bar[it] + bar_off);
-        }
-      }
-    }
-    if (a.h_all != nullptr && w < G && (b0 + w) < B && lane < U && (u0 + lane) < N) {
-      const long long o = ((long long)s * B + (b0 + w)) * N + u0 + lane;
-      a.h_all[o] = stage[w * 32 + lane];
-      if (a.g_r != nullptr) {
-        a.g_r[o] = stage[(1 * G + w) * 32 + lane];
-        a.g_z[o] = stage[(2 * G + w) * 32 + lane];
-        a.g_n[o] = stage[(3 * G + w) * 32 + lane];
-        a.g_hn[o] = stage[(4 * G + w) * 32 + lane];
-      }
-    }
-    wk_s = nx_wk; wq_s = nx_wq;
-    __syncthreads();
-  }
-  cluster.sync();
-
-#pragma unroll
-  for (int i = 0; i < UPW; ++i) {
-    if (fin[i] && bvalid) {
-      const int u = u0 + w * UPW + i;
-      a.key[(long long)(b0 + fb) * N + u] = key_acc[i];
-      a.query[(long long)(b0 + fb) * N + u] = query_acc[i];
-    }
-  }
-}
-
-template <int JC, int UPW, int CS, int G>
-static int launch_gru_cluster_uw(const GruArgs& a, cudaStream_t st) {
-  constexpr int KP = 128 * JC;
-  constexpr int ULOC = GRU_WARPS * UPW;
-  const size_t smem = (size_t)(3 * ULOC * KP + 2 * G * KP + 5 * G * 32) * sizeof(float) + 2 * sizeof(uint64_t);
-  if (smem > 227 * 1024) return -1;
-  auto kern = gru_cluster_uw_kernel<JC, UPW, CS, G>;
-  static bool attr_set = false;
-  static int max_clusters = 0;
-  const int nclusters = ceil_div(a.B, G);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * CS);
-  cfg.blockDim = dim3(GRU_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (!attr_set) {
-    SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CS > 8) SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-    if (e != cudaSuccess) {
-      (void)cudaGetLastError();
-      max_clusters = 0;
-    }
-    attr_set = true;
-  }
-  if (max_clusters < 1) return -1;
-  ProfileHook* hook = profile_hook();
-  if (hook->start != nullptr) SG_CUDA(cudaEventRecord(hook->start, st));
-  SG_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
-  if (hook->stop != nullptr) SG_CUDA(cudaEventRecord(hook->stop, st));
-  count_launch();
-  return 0;
-}
-
-template <int G>
-static int dispatch_gru_cluster_uw(const GruArgs& a, cudaStream_t st) {
-  constexpr int CS = 16;
-  const int U = ceil_div(a.N, CS);
-  const int upw = ceil_div(U, GRU_WARPS);
-  const int jc = ceil_div(CS * ((U + 3) & ~3), 128);
-  if (upw > 4 || jc > 4) return -1;
-#define SG_GRU_CASE(J, P) \
-  if (jc == J && upw == P) return launch_gru_cluster_uw<J, P, CS, G>(a, st);
-  SG_GRU_CASE(1, 1) SG_GRU_CASE(1, 2) SG_GRU_CASE(1, 3) SG_GRU_CASE(1, 4)
-  SG_GRU_CASE(2, 1) SG_GRU_CASE(2, 2) SG_GRU_CASE(2, 3) SG_GRU_CASE(2, 4)
-  SG_GRU_CASE(3, 1) SG_GRU_CASE(3, 2) SG_GRU_CASE(3, 3) SG_GRU_CASE(3, 4)
-  SG_GRU_CASE(4, 1) SG_GRU_CASE(4, 2) SG_GRU_CASE(4, 3) SG_GRU_CASE(4, 4)
-#undef SG_GRU_CASE
-  return -1;
 }
 
 // returns 0 launched, -1 configuration not launchable here, >0 error
@@ -1083,31 +814,15 @@ int gru_keyquery_forward(const GruArgs& a_in, int path, float* scratch, cudaStre
   }
   SG_TRY(gru_input_proj(a, st));
   if (path != 1) {
-    // 16-CTA clusters with one group of 4 (or 5, to stay within the 7 resident clusters of a B200)
-    // sequences each.  STEMGNN_GRU_MODE=ng*10+g forces a configuration, incl. the two-group pipelined
-    // variants 22 / 23 (tests, measurements).
-    int force = 0;
-    if (const char* e = getenv("STEMGNN_GRU_MODE")) force = atoi(e);
+    // 16-CTA clusters with one group of 4 (or 5, to stay within the 7 resident clusters of a B200) sequences each.
+    // (The two-group software-pipelined and the unit-wise variants of round 1 measured slower and were removed;
+    // profiles/README.md keeps their numbers.)
     int max_active = 0;
     int rc = dispatch_gru_cluster<16, 1, 4>(a, st, &max_active);
     if (rc == 0) {
       const int mx = max_active > 0 ? max_active : 1;
-      int mode = force;
-      if (mode == 0) {
-        // measured on B200 (profiles/README.md): one group of 5 sequences in a single wave beats both
-        // 4 sequences in two waves and two software-pipelined groups (the DSMEM stores of one group
-        // stall the LDS-heavy mat-vec of the other), so the pipelined modes are opt-in only.
-        if (ceil_div(a.B, 4) <= mx) mode = 14;
-        else if (ceil_div(a.B, 5) <= mx) mode = 15;
-        else mode = 14;
-      }
-      static const bool uw = getenv("STEMGNN_GRU_UW") != nullptr;   // unit-wise step: opt-in (measured slower)
-      if (uw && mode == 15) rc = dispatch_gru_cluster_uw<5>(a, st);
-      else if (uw && mode == 14) rc = dispatch_gru_cluster_uw<4>(a, st);
-      else if (mode == 22) rc = dispatch_gru_cluster<16, 2, 2>(a, st, nullptr);
-      else if (mode == 23) rc = dispatch_gru_cluster<16, 2, 3>(a, st, nullptr);
-      else if (mode == 15) rc = dispatch_gru_cluster<16, 1, 5>(a, st, nullptr);
-      else rc = dispatch_gru_cluster<16, 1, 4>(a, st, nullptr);
+      const bool g5 = ceil_div(a.B, 4) > mx && ceil_div(a.B, 5) <= mx;     // one wave beats two
+      rc = g5 ? dispatch_gru_cluster<16, 1, 5>(a, st, nullptr) : dispatch_gru_cluster<16, 1, 4>(a, st, nullptr);
       if (rc < 0) rc = dispatch_gru_cluster<16, 1, 4>(a, st, nullptr);
       if (rc == 0) return 0;
       if (rc > 0) return rc;

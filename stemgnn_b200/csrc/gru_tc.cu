@@ -471,27 +471,31 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
 #pragma unroll
     for (int i = 0; i < PP; ++i) input_proj(0, i, gi_r[i], gi_z[i], gi_n[i]);
 
-    // step-invariant send descriptors: granule = (array hi/lo, sequence b, 8 units); destinations in the rotated
-    // order (q + i) % CS so that the slices a CTA receives arrive staggered and its MMAs can start early
-    const int gran_per_b = U >> 3;
-    const int n_gran = 2 * G * gran_per_b;
-    const int n_send = n_gran * CS;
-    constexpr int SEND_ITEMS = (2 * GT_GMAX * 5 * 16 + GT_EPI - 1) / GT_EPI;     // U <= 40, CS <= 16
-    uint32_t snd_src[SEND_ITEMS], snd_dst[SEND_ITEMS], snd_bar[SEND_ITEMS];
+    // step-invariant send descriptors.  A granule = 8 consecutive units of one sequence in one array (hi / lo) = 16 bytes of
+    // the destination's B tile.  Pair p = et + 128 i maps 8-aligned groups of lanes to granules (U % 8 == 0), so every granule
+    // is produced inside ONE warp: the warp that computed it sends it to all CS CTAs after a __syncwarp — no block-wide
+    // barrier between the gate math and the sends.  Per (warp, i): 4 lane groups x 2 arrays = 8 granules x CS destinations,
+    // visited slot-major in the rotated order (q + slot) % CS so that the slices a CTA receives arrive staggered.
+    constexpr int SEND_K = (8 * 16 + 31) / 32;               // sends per lane per i (CS <= 16)
+    uint32_t snd_src[PP][SEND_K], snd_dst[PP][SEND_K], snd_bar[PP][SEND_K];
 #pragma unroll
-    for (int it = 0; it < SEND_ITEMS; ++it) {
-      const int idx = et + it * GT_EPI;
-      snd_src[it] = 0xFFFFFFFFu;
-      snd_dst[it] = snd_bar[it] = 0;
-      if (idx < n_send) {
-        const int slot = idx / n_gran, gr = idx - slot * n_gran;
-        const int dest = (q + slot) % CS;
-        const int arr = gr / (G * gran_per_b), rem = gr - arr * (G * gran_per_b);
-        const int bb = rem / gran_per_b, g8 = rem - bb * gran_per_b;
-        snd_src[it] = (uint32_t)(((arr * GT_GMAX + bb) * U + 8 * g8) * 2);                  // bytes into stage_sm
-        const uint32_t off = sw128_off(arr * 8 + bb, u0 + 8 * g8, B_CHUNK_BYTES);
-        snd_dst[it] = map_cta(s_u32(B_sm) + off, (uint32_t)dest);
-        snd_bar[it] = map_cta(s_u32(&hbar[q]), (uint32_t)dest);        // the destination's barrier for source q
+    for (int i = 0; i < PP; ++i) {
+#pragma unroll
+      for (int k = 0; k < SEND_K; ++k) {
+        const int j = lane + 32 * k;
+        const int slot = j >> 3, gran = j & 7;
+        const int arr = gran >> 2;
+        const int p0 = 32 * (warp - GT_ROUNDS) + GT_EPI * i + 8 * (gran & 3);     // first pair of the lane group
+        snd_src[i][k] = 0xFFFFFFFFu;
+        snd_dst[i][k] = snd_bar[i][k] = 0;
+        if (slot < CS && p0 < U * G) {
+          const int bb = p0 / U, lu0 = p0 - bb * U;
+          const int dest = (q + slot) % CS;
+          snd_src[i][k] = (uint32_t)(((arr * GT_GMAX + bb) * U + lu0) * 2);                 // bytes into stage_sm
+          const uint32_t off = sw128_off(arr * 8 + bb, u0 + lu0, B_CHUNK_BYTES);
+          snd_dst[i][k] = map_cta(s_u32(B_sm) + off, (uint32_t)dest);
+          snd_bar[i][k] = map_cta(s_u32(&hbar[q]), (uint32_t)dest);    // the destination's barrier for source q
+        }
       }
     }
     float wk_s = __ldg(a.wk + 0), wq_s = __ldg(a.wq + 0);
@@ -577,16 +581,20 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
       wk_s = nx_wk; wq_s = nx_wq;
       GT_STAMP(9);
       if (s + 1 < N) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __syncwarp();                  // the granules this warp sends were staged by its own lanes
         GT_STAMP(10);
         const uint32_t dst_off = (uint32_t)nxt * b_buf, bar_off = (uint32_t)nxt * 16u * 8u;
 #pragma unroll
-        for (int it = 0; it < SEND_ITEMS; ++it) {
-          if (snd_src[it] != 0xFFFFFFFFu) {
-            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage_sm) + snd_src[it]);
-            st_async_16(snd_dst[it] + dst_off, v, snd_bar[it] + bar_off);
+        for (int k = 0; k < SEND_K; ++k) {
+#pragma unroll
+          for (int i = 0; i < PP; ++i) {
+            if (snd_src[i][k] != 0xFFFFFFFFu) {
+              const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage_sm) + snd_src[i][k]);
+              st_async_16(snd_dst[i][k] + dst_off, v, snd_bar[i][k] + bar_off);
+            }
           }
         }
+        __syncwarp();                  // stage entries are rewritten by the next step's gate phase of this warp
       }
       GT_STAMP(11);
     }

@@ -75,7 +75,7 @@ struct HeadArgs {
   int R, N, T, W;
 };
 int launch_gft(const float* mul_L, const float* x_bwn, float* G, float* skbuf, int B, int N, int W,
-               cudaStream_t st);
+               cudaStream_t st, unsigned short* g_img = nullptr, int ldh = 0, int bf16 = 0, int* g_ready = nullptr);
 int launch_block_head(const HeadArgs& a, cudaStream_t st);
 int launch_model_head(const float* f0, const float* f1, const float* w0, const float* b0,
                       const float* w2, const float* b2, float* out, int B, int N, int W, int H,
@@ -102,7 +102,7 @@ size_t glu_chain_h_scratch_halves(int M, int N, int K1);
 int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const float* const w[3][2],
                 const float* const bias[3][2], float* out3, int ldo3, float* const act[2], float* const save_l[3],
                 float* const save_s[3], unsigned short* scratch, int reuse_w, const unsigned short* g_shared,
-                cudaStream_t st);
+                cudaStream_t st, int g_ready = 0);
 
 // generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,

@@ -9,6 +9,9 @@
 //     irfft(onesided=False) reads bins 0..T/2 only and ignores Im(DC), Im(Nyquist),
 //     which shows up here as exactly-zero rows of the folded matrix.
 // What remains per row are plain GEMMs (gemm.cuh / glu_tc.cu) plus the small head kernels below.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "internal.cuh"
 #include "gemm.cuh"
@@ -93,8 +96,42 @@ __global__ void gft_reduce_scatter_kernel(const float* __restrict__ P, int ks, f
   G[idx] = acc;
 }
 
+// same reduction, additionally emitting the 16-bit operand images of G the kind::f16 GLU chain reads (row pitch `ldh`
+// halves, zero padded): mode 0 = fp16 hi/lo split, 1 = bf16 (hi only).  One thread per image element.
+__global__ void gft_reduce_scatter_h_kernel(const float* __restrict__ P, int ks, float* __restrict__ G, int B, int N, int W,
+                                            unsigned short* __restrict__ g_hi, unsigned short* __restrict__ g_lo, int ldh,
+                                            int bf16) {
+  const long long total = (long long)B * N * ldh;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % ldh);
+  const long long bn = idx / ldh;
+  unsigned short hi = 0, lo = 0;
+  if (c < 3 * W) {
+    const int t = c % W, kp = c / W;
+    const int n = (int)(bn % N), b = (int)(bn / N);
+    const long long src = ((long long)kp * N + n) * ((long long)B * W) + (long long)b * W + t;
+    const long long stride = (long long)3 * N * B * W;
+    float acc = 0.f;
+    for (int z = 0; z < ks; ++z) acc += P[(long long)z * stride + src];
+    G[bn * (3 * W) + c] = acc;
+    if (bf16) {
+      hi = __bfloat16_as_ushort(__float2bfloat16_rn(acc));
+    } else {
+      const float xs = fminf(fmaxf(acc, -65504.f), 65504.f);
+      const __half h = __float2half_rn(xs);
+      hi = __half_as_ushort(h);
+      lo = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
+    }
+  }
+  g_hi[idx] = hi;
+  if (!bf16) g_lo[idx] = lo;
+}
+
+// g_img != nullptr: also write the 16-bit images [hi (B*N x ldh) | lo] for the tensor-core chain; *g_ready tells the caller
 int launch_gft(const float* mul_L, const float* x_bwn, float* G, float* skbuf, int B, int N, int W,
-               cudaStream_t st) {
+               cudaStream_t st, unsigned short* g_img, int ldh, int bf16, int* g_ready) {
+  if (g_ready != nullptr) *g_ready = 0;
   // A = mul_L[1..3] viewed as (3N x N); B operand = x (B*W x N) read as B[n*ldb + k]
   // (3N x N) . (N x B*W) fills only ~54 CTAs: deterministic split-K (partials + fixed-order reduction)
   const int ks = skbuf != nullptr ? pick_ksplit(3 * N, B * W, N) : 1;
@@ -102,6 +139,14 @@ int launch_gft(const float* mul_L, const float* x_bwn, float* G, float* skbuf, i
     GemmOperands g = {mul_L + (long long)N * N, N, 0, x_bwn, N, 0, nullptr, 3 * N, B * W, N, ks};
     EpiPartial epi = {skbuf, B * W, (long long)3 * N * B * W};
     SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "gft_gemm_splitk")));
+    if (g_img != nullptr) {
+      const long long total = (long long)B * N * ldh;
+      gft_reduce_scatter_h_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(skbuf, ks, G, B, N, W, g_img,
+                                                                              g_img + (size_t)B * N * ldh, ldh, bf16);
+      SG_LAUNCH_CHECK("gft_reduce_scatter_h_kernel");
+      if (g_ready != nullptr) *g_ready = 1;
+      return 0;
+    }
     const long long total = (long long)B * N * 3 * W;
     gft_reduce_scatter_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(skbuf, ks, G, B, N, W);
     SG_LAUNCH_CHECK("gft_reduce_scatter_kernel");
