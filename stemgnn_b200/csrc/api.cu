@@ -1,6 +1,7 @@
 // C ABI of stemgnn_b200 (see include/stemgnn_b200.h): workspace carving + forward orchestration.
 // Every kernel is launched on the caller's stream; nothing here allocates device memory.
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -18,8 +19,8 @@ void set_error(const char* fmt, ...) {
 }
 void clear_error() { g_err[0] = 0; }
 
-static long long g_launches = 0;           // one host thread drives one device (process per GPU)
-void count_launch() { ++g_launches; }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static ProfileHook g_hook = {nullptr, nullptr};
 ProfileHook* profile_hook() { return &g_hook; }
 
@@ -317,7 +318,7 @@ extern "C" {
 int stemgnn_version(void) { return STEMGNN_ABI_VERSION; }
 const char* stemgnn_last_error(void) { return g_err; }
 
-long long stemgnn_launch_count(void) { return g_launches; }
+long long stemgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* stemgnn_gru_kernel_name(void) { return gru_tc_kernel_name(); }
 
 void stemgnn_profile_gru(void* start_event, void* stop_event) {

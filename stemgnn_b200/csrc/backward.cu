@@ -694,7 +694,10 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
     SG_CUDA(cudaMemsetAsync(w.dh[0], 0, (size_t)R * sizeof(float), st));
     const size_t smem = (size_t)(4 * 3 * N + 4 * N + 8 * 4 * 32) * sizeof(float);
     SG_CHECK(smem <= 200 * 1024, "gru backward: N=%d too large for the step kernel", N);
-    static size_t smem_set = 0;
+    static size_t smem_set_dev[64] = {};   // function attributes are per device
+  int dev_ = 0;
+  (void)cudaGetDevice(&dev_);
+  size_t& smem_set = smem_set_dev[dev_ & 63];
     if (smem > smem_set) {
       SG_CUDA(cudaFuncSetAttribute(gru_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;
@@ -727,6 +730,9 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
         rc = tc_gemm(3 * N, npad, Kr, 1.f, w.dghT, ldT, w.hT + (size_t)n0 * ldT, ldT, nn_, gr.gru_w_hh + n0, nullptr,
                      0, N, nn_, 1, 8, st);
         if (rc > 0) return rc;
+        // a chunk that is unsupported AFTER earlier chunks were accumulated must not fall back to the full fp32 product
+        // (it would double-count the finished columns)
+        SG_CHECK(!(rc < 0 && n0 > 0), "d_gru_w_hh: tensor-core column chunk at %d unsupported after earlier chunks ran", n0);
       }
       SG_CHECK(rc == 0 || rc == -1, "tc dW_hh");
     }

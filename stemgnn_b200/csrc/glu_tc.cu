@@ -651,7 +651,10 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
   const size_t smem = (size_t)nstage * ((size_t)TC_BM * bk * 4 + 2 * (size_t)N * bk * 4) + 128 +
                       2 * (size_t)N * sizeof(float) + 1024;
   if (smem > 227 * 1024) return -1;
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[64] = {};   // function attributes are per device
+  int dev_ = 0;
+  (void)cudaGetDevice(&dev_);
+  size_t& smem_set = smem_set_dev[dev_ & 63];
   if (smem > smem_set) {
     SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SG_CUDA(cudaFuncSetAttribute(glu_tc_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -691,7 +694,10 @@ int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const flo
   if (!make_map(enc, &ma, A, M, K, lda, TC_BM) || !make_map(enc, &mb, B, n_rows_b, K, ldb, N)) return -1;
   const size_t smem = (size_t)3 * (TC_BM * 128 + (size_t)N * 128) + 64 + 1024;
   if (smem > 227 * 1024) return -1;
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[64] = {};   // function attributes are per device
+  int dev_ = 0;
+  (void)cudaGetDevice(&dev_);
+  size_t& smem_set = smem_set_dev[dev_ & 63];
   if (smem > smem_set) {
     SG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
@@ -729,7 +735,10 @@ int glu_chain_tc(int M, int N, int K1, const float* G, int ldg, const float* con
     }
   const size_t smem = (size_t)8 * TC_BM * 128 + (size_t)3 * 2 * N * 64 + 128 + (size_t)6 * N * sizeof(float) + 1024;
   if (smem > 227 * 1024) return -1;
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[64] = {};   // function attributes are per device
+  int dev_ = 0;
+  (void)cudaGetDevice(&dev_);
+  size_t& smem_set = smem_set_dev[dev_ & 63];
   if (smem > smem_set) {
     SG_CUDA(cudaFuncSetAttribute(glu_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;

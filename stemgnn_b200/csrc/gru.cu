@@ -376,8 +376,12 @@ static int launch_gru_cluster(const GruArgs& a, cudaStream_t st, int* max_active
   const size_t smem = (size_t)(3 * ULOC * KP + NG * 2 * G * KP + NG * 5 * G * 32 + GRU_WARPS * V + 2) * sizeof(float) +
                       NG * 2 * sizeof(uint64_t);
   auto kern = gru_cluster_kernel<JC, UPW, CS, NG, G>;
-  static bool attr_set = false;   // one process drives one device (DDP = process per GPU)
-  static int max_clusters = 0;
+  static bool attr_set_dev[64] = {};      // function attributes / occupancy are per device
+  static int max_clusters_dev[64] = {};
+  int dev_ = 0;
+  (void)cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
+  int& max_clusters = max_clusters_dev[dev_ & 63];
   const int nclusters = ceil_div(a.B, NG * G);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
@@ -632,8 +636,12 @@ static int launch_gru_bwd_cluster(const GruBwdClusterArgs& a, cudaStream_t st) {
                       2 * sizeof(uint64_t);
   if (smem > 227 * 1024) return -1;
   auto kern = gru_bwd_cluster_kernel<JC, UPW, CS, G>;
-  static bool attr_set = false;
-  static int max_clusters = 0;
+  static bool attr_set_dev[64] = {};
+  static int max_clusters_dev[64] = {};
+  int dev_ = 0;
+  (void)cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
+  int& max_clusters = max_clusters_dev[dev_ & 63];
   const int nclusters = ceil_div(a.B, G);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
