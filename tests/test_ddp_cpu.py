@@ -37,7 +37,9 @@ def _worker(rank, world, port, q):
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
     buf = torch.arange(4, dtype=torch.float32) + rank
     ddp.allreduce_mean_(buf)
-    q.put((rank, [t.clone() for t in ref], flat.clone(), idx, buf.clone()))
+    # numpy payloads are pickled by value: torch tensors would travel as shared-memory file descriptors, which
+    # vanish if this worker exits before the parent has read the queue
+    q.put((rank, [t.numpy().copy() for t in ref], flat.detach().numpy().copy(), idx, buf.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,6 +55,8 @@ def test_two_rank_gloo_allreduce_and_sharding():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    out = [(r, [torch.from_numpy(t) for t in ps], torch.from_numpy(g), i, torch.from_numpy(b))
+           for r, ps, g, i, b in out]
     (_, p0, g0, i0, b0), (_, p1, g1, i1, b1) = out
     for a, b in zip(p0, p1):
         assert torch.equal(a, b)                               # broadcast made the replicas identical
