@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STEMGNN_ABI_VERSION 2
+#define STEMGNN_ABI_VERSION 3
 #define STEMGNN_K 4            /* Chebyshev order "3 + 1", base_model.py:23 */
 #define STEMGNN_MAX_STACK 2    /* Model.forward hard-codes result[0] + result[1], base_model.py:174 */
 
@@ -92,6 +92,12 @@ typedef struct {
   float* fc0_w; float* fc0_b; float* fc2_w; float* fc2_b;
 } stemgnn_grads_t;
 
+/* Data-parallel hook for the latent graph (optional).  Called on the HOST while the library is issuing its launches on
+ * `stream`; the callee must enqueue, in stream order on `stream`, the replacement of dev_buf[0..n) by its MEAN over all ranks
+ * (an NCCL all-reduce).  With it every replica builds the graph of the GLOBAL batch (`torch.mean(attention, dim=0)`,
+ * base_model.py:140, over all shards) instead of its own shard's. */
+typedef void (*stemgnn_allreduce_fn)(float* dev_buf, long long n, void* user, stemgnn_stream_t stream);
+
 /* Options of one forward call. */
 typedef struct {
   float leaky_alpha;        /* LeakyReLU slope of the attention, base_model.py:102 (0.2) */
@@ -110,6 +116,10 @@ typedef struct {
                                1 = eigendecomposition (fused Laplacian + Jacobi kernel) and U p(Lambda) U^T — eval only */
   const unsigned long long* dropout_offset_dev; /* optional DEVICE counter added to dropout_offset when the kernels run
                                (NULL = none): lets a captured CUDA graph draw a fresh mask on every replay */
+  stemgnn_allreduce_fn graph_allreduce; /* NULL = each replica uses its own shard's graph.  Forward: called on the batch-mean
+                               attention (N*N) and its degree vector (N) before the Laplacian is formed; backward: called on the
+                               gradient w.r.t. that attention (N*N) before it enters the softmax backward */
+  void* graph_allreduce_user; /* passed through to graph_allreduce */
 } stemgnn_fwd_opts_t;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -234,6 +244,18 @@ int stemgnn_counters_tick(unsigned long long* step_dev, unsigned long long* drop
 int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int a_kmajor,
                   const float* B, int ldb, int b_nk, float beta, float* C, int ldc,
                   stemgnn_stream_t stream);
+
+/* C[M,N] = A(M,K) * B(N,K)^T on the tcgen05 kind::tf32 GEMM (test hook of csrc/spec_tc.cu).  A[m*lda+k], B[n*ldb+k];
+ * lda, ldb multiples of 4, A and B 16-byte aligned, N a multiple of 16 in [16,256].  split_ops: 1 = 3xTF32 split operands
+ * (hi/lo split inside the kernel, fp32-level result), 0 = one pass on the raw fp32 bits (TF32-level). */
+int stemgnn_tc_gemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                    int split_ops, stemgnn_stream_t stream);
+
+/* Graph Fourier transform of one block input (base_model.py:63) on tcgen05 with 3xTF32 split operands (test hook):
+ * G[(b*N + n)*3W + k*W + t] = sum_m mul_L[k+1][n][m] * x[b][t][m],  k = 0..2.   mul_L (4,N,N), x (B,W,N), G (B*N, 3W);
+ * scratch: 4*N*pad4(N) + B*W*pad4(N) floats (the TMA-able operand copies), 16-byte aligned. */
+int stemgnn_gft_forward(const float* mul_L, const float* x, float* G, int B, int N, int W, float* scratch,
+                        stemgnn_stream_t stream);
 
 /* out[M,N] = (A W_l^T + b_l) * sigmoid(A W_r^T + b_r)  (GLU, base_model.py:12-13) on the tcgen05
  * TF32 tensor-core kernel (use_tc=1) or the fp32 FFMA2 kernel (use_tc=0).  A (M,K) lda; W (N,K). */

@@ -8,7 +8,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libstemgnn_b200.so")
 
 MAX_STACK = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Dims(Structure):
@@ -32,10 +32,15 @@ class ModelPtrs(Structure):
                 ("fc2_w", c_void_p), ("fc2_b", c_void_p)]
 
 
+# stemgnn_allreduce_fn(dev_buf, n, user, stream)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(None, c_void_p, ctypes.c_longlong, c_void_p, c_void_p)
+
+
 class FwdOpts(Structure):
     _fields_ = [("leaky_alpha", c_float), ("dropout_p", c_float), ("training", c_int),
                 ("dropout_seed", c_uint64), ("dropout_offset", c_uint64), ("dropout_mask", c_void_p),
-                ("gemm_mode", c_int), ("reuse_folded", c_int), ("graph_mode", c_int), ("dropout_offset_dev", c_void_p)]
+                ("gemm_mode", c_int), ("reuse_folded", c_int), ("graph_mode", c_int), ("dropout_offset_dev", c_void_p),
+                ("graph_allreduce", ALLREDUCE_FN), ("graph_allreduce_user", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/stemgnn_b200.h declares
@@ -75,6 +80,8 @@ SYMBOLS = {
     "stemgnn_counters_tick": (c_int, [c_void_p, c_void_p, ctypes.c_ulonglong, c_void_p]),
     "stemgnn_sgemm": (c_int, [c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_float, c_void_p, c_int, c_void_p]),
+    "stemgnn_tc_gemm": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "stemgnn_gft_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "stemgnn_glu_gemm": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }

@@ -44,8 +44,14 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
   ws.mul_L = take(4 * N * N);
   ws.attention = take(N * N);
   ws.gru_scratch = take(2 * R);
-  ws.gi = take(N * R * 3);
+  // input projection of the FFMA2 fallback (N, B, 3N) — and, on the tensor-core path, the packed fp16 hi/lo W_hh images,
+  // which are LARGER than the projection for tiny batches (B*N of a few rows): size for both
+  const size_t gi_img = (gru_tc_image_bytes(dm.N, dm.W) + sizeof(float) - 1) / sizeof(float);
+  ws.gi = take(N * R * 3 > gi_img ? N * R * 3 : gi_img);
   ws.skbuf = take(8 * (N * N > 3 * N * B * W ? N * N : 3 * N * B * W));
+  const size_t Np = (size_t)pad4(dm.N);
+  ws.mul_Lp = take(3 * N * Np);
+  ws.x_pad = take(B * W * Np);
   ws.eig_lambda = take(N + 2);
   ws.eig_U = take((N + 2) * (N + 2));
   ws.eig_S = take((N + 2) * (N + 2));
@@ -71,6 +77,7 @@ Workspace carve_workspace(const stemgnn_dims_t& dm, int training, float* base) {
     b.forecast = take(R * W);
     b.bc_bnw = take(R * W);
     b.bc_bwn = take(R * W);
+    b.bc_pad = take(B * W * Np);
     for (int g = 0; g < 6; ++g) {
       b.save_l[g] = training ? take(R * d) : nullptr;
       b.save_s[g] = training ? take(R * d) : nullptr;
@@ -205,32 +212,30 @@ int glu_chain(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int nc
 }
 
 // StockBlockLayer.forward (base_model.py:61-75)
+// mul_Lp / x_pad: TMA-able copies ((3N, pad4(N)) = mul_L[1..3], (B*W, pad4(N)) = the block input) or null
 int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, int stack_idx,
                   int gemm_mode, int reuse_folded, const float* x_bnw, const float* x_bwn,
-                  const float* mul_L, const BlockWs& b, float* skbuf, cudaStream_t st) {
+                  const float* mul_L, const BlockWs& b, float* skbuf, cudaStream_t st,
+                  const float* mul_Lp = nullptr, const float* x_pad = nullptr) {
   const int B = dm.B, N = dm.N, W = dm.W, T = dm.multi * W, d = 4 * T, R = B * N;
   const int PW = (stack_idx == 0) ? T + W : T;
   if (!reuse_folded) SG_TRY(fold_block_weights(dm, bp, stack_idx, 1, 3, b, st));
-  // the split-K reduction of the graph-Fourier GEMM also emits the 16-bit operand images of G for the kind::f16 chain
   int g_ready = 0;
   static const bool no_h = getenv("STEMGNN_GLU_NO_F16") != nullptr;
   const bool h_chain = (gemm_mode == 0 || gemm_mode == 3) && !no_h && d % 16 == 0 && d <= 256 && 3 * W <= 256;
-  SG_TRY(launch_gft(mul_L, x_bwn, b.G, skbuf, B, N, W, st,
-                    h_chain ? reinterpret_cast<unsigned short*>(b.hscratch[0]) : nullptr, (3 * W + 63) / 64 * 64,
-                    gemm_mode == 3 ? 1 : 0, &g_ready));
+  unsigned short* g_img = h_chain ? reinterpret_cast<unsigned short*>(b.hscratch[0]) : nullptr;
+  const int ldh = (3 * W + 63) / 64 * 64;
+  // default / bf16 modes: the graph Fourier transform on tcgen05 (3xTF32 split operands in the default mode), its
+  // epilogue writes the rows of G and the 16-bit operand images the kind::f16 GLU chain reads
+  const bool tc3 = gemm_mode == 0 || gemm_mode == 3;
+  const int split_ops = gemm_mode == 0 ? 1 : 0;
+  int rc_gft = -1;
+  if (tc3) rc_gft = gft_tc(mul_Lp, pad4(N), x_pad, pad4(N), b.G, g_img, ldh, gemm_mode == 3 ? 1 : 0, B, N, W, split_ops, st);
+  if (rc_gft > 0) return rc_gft;
+  if (rc_gft == 0) g_ready = g_img != nullptr ? 1 : 0;
+  else   // fp32 FFMA2 split-K GEMM; its reduction also emits the operand images
+    SG_TRY(launch_gft(mul_L, x_bwn, b.G, skbuf, B, N, W, st, g_img, ldh, gemm_mode == 3 ? 1 : 0, &g_ready));
   SG_TRY(glu_chain(dm, bp, 3 * W, gemm_mode, b, st, reuse_folded, g_ready));
-  {   // pre = [real3 | imag3] @ woutT^T : tcgen05 TF32 unless exact fp32 is requested
-    int rc = -1;
-    if (gemm_mode != 1)
-      rc = tc_gemm(R, (PW + 15) / 16 * 16, 2 * d, 1.f, b.act3, 2 * d, b.wout, 2 * d, (PW + 15) / 16 * 16, b.pre,
-                   nullptr, 0, PW, PW, 0, 1, st);
-    if (rc > 0) return rc;
-    if (rc < 0) {   // exact fp32 requested, or a shape outside the tensor-core kernel's envelope
-      GemmOperands g = {b.act3, 2 * d, 0, b.wout, 2 * d, 0, nullptr, R, PW, 2 * d};
-      EpiAxpby epi = {b.pre, PW, 0, nullptr, 0, 0, 1.f, 0.f};
-      SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "out_gemm")));
-    }
-  }
   HeadArgs h = {};
   h.pre = b.pre; h.ldp = PW; h.x_bnw = x_bnw;
   h.bf = bp.forecast_b; h.wfr = bp.forecast_result_w; h.bfr = bp.forecast_result_b;
@@ -240,7 +245,27 @@ int block_forward(const stemgnn_dims_t& dm, const stemgnn_block_params_t& bp, in
     h.bb = bp.backcast_b; h.wsc = bp.shortcut_w; h.bsc = bp.shortcut_b;
     h.backcast_bnw = b.bc_bnw; h.backcast_bwn = b.bc_bwn;
   }
-  return launch_block_head(h, st);
+  if (tc3) {   // folded output map + sigmoid heads in one launch (the pre-activations never leave tensor memory)
+    const int rc = out_head_tc(b.act3, 2 * d, b.wout, (PW + 15) / 16 * 16, h, b.bc_pad, pad4(N), split_ops, st);
+    if (rc == 0) return 0;
+    if (rc > 0) return rc;
+  }
+  {   // pre = [real3 | imag3] @ woutT^T : tcgen05 TF32 unless exact fp32 is requested
+    int rc = -1;
+    if (gemm_mode != 1)
+      rc = tc_gemm(R, (PW + 15) / 16 * 16, 2 * d, 1.f, b.act3, 2 * d, b.wout, 2 * d, (PW + 15) / 16 * 16, b.pre,
+                   nullptr, 0, PW, PW, 0, 1, st, gemm_mode == 0 ? -1 : 0);
+    if (rc > 0) return rc;
+    if (rc < 0) {   // exact fp32 requested, or a shape outside the tensor-core kernel's envelope
+      GemmOperands g = {b.act3, 2 * d, 0, b.wout, 2 * d, 0, nullptr, R, PW, 2 * d};
+      EpiAxpby epi = {b.pre, PW, 0, nullptr, 0, 0, 1.f, 0.f};
+      SG_TRY((launch_sgemm<false, true, false>(g, epi, 1, st, "out_gemm")));
+    }
+  }
+  SG_TRY(launch_block_head(h, st));
+  if (stack_idx == 0 && tc3)   // the next block's tcgen05 GFT reads the padded copy
+    SG_TRY(launch_pad_rows(b.bc_bwn, (long long)B * W, N, N, b.bc_pad, pad4(N), st));
+  return 0;
 }
 
 static int check_block_params(const stemgnn_block_params_t* bp, int stack_idx) {
@@ -257,13 +282,17 @@ static int check_block_params(const stemgnn_block_params_t* bp, int stack_idx) {
 }
 
 // C[i] = alpha * sum_z P[z][i] + beta * Cin[i]   (fixed summation order)
+// C2 (optional): second copy with row pitch ld2 (rows of `ncols` elements)
 __global__ void splitk_reduce_kernel(const float* __restrict__ P, int ks, int n, float alpha,
-                                     const float* __restrict__ Cin, float beta, float* __restrict__ C) {
+                                     const float* __restrict__ Cin, float beta, float* __restrict__ C,
+                                     float* __restrict__ C2, int ncols, int ld2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
   for (int z = 0; z < ks; ++z) acc += P[(long long)z * n + i];
-  C[i] = alpha * acc + (Cin != nullptr ? beta * Cin[i] : 0.f);
+  const float v = alpha * acc + (Cin != nullptr ? beta * Cin[i] : 0.f);
+  C[i] = v;
+  if (C2 != nullptr) C2[(long long)(i / ncols) * ld2 + i % ncols] = v;
 }
 
 int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const float* key,
@@ -279,13 +308,19 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
   a.B = B; a.N = N;
   SG_CHECK(op.dropout_p >= 0.f && op.dropout_p < 1.f, "dropout_p=%f outside [0,1)", op.dropout_p);
   SG_TRY(launch_attention(a, ws.qmax, st));
-  SG_TRY(launch_laplacian(ws.a_raw, ws.deg, attention, ws.mul_L, N, st));
+  if (op.graph_allreduce != nullptr) {   // data parallel, global-batch graph: mean over ranks of the shard means
+    op.graph_allreduce(ws.a_raw, (long long)N * N, op.graph_allreduce_user, st);
+    op.graph_allreduce(ws.deg, N, op.graph_allreduce_user, st);
+  }
+  const int Np = pad4(N);      // ws.mul_Lp: (3N, Np) copy of mul_L[1..3] for the tcgen05 graph Fourier transform
+  SG_TRY(launch_laplacian(ws.a_raw, ws.deg, attention, ws.mul_L, N, st, ws.mul_Lp, Np));
   const size_t nn = (size_t)N * N;
   if (op.graph_mode == 1 && !op.training && N >= 2 && N <= 512) {
     // opt-in eigendecomposition path (north_star; the reference's dead `graph_fft` hook): L = U Lambda U^T by the fused
     // Laplacian + Jacobi kernel, polynomial stack rebuilt as U p(Lambda) U^T
     SG_TRY(laplacian_eig(ws.a_raw, ws.deg, N, ws.eig_lambda, ws.eig_U, ws.eig_info, 30, 1e-6f, st));
-    return eig_poly_stack(ws.eig_lambda, ws.eig_U, N, ws.eig_S, ws.mul_L, st);
+    SG_TRY(eig_poly_stack(ws.eig_lambda, ws.eig_U, N, ws.eig_S, ws.mul_L, st));
+    return launch_pad_rows(ws.mul_L + nn, 3ll * N, N, N, ws.mul_Lp, Np, st);
   }
   // the two N^3 Chebyshev products fill only a few CTAs: deterministic split-K (partials + ordered reduce)
   const int ks = pick_ksplit(N, N, N);
@@ -298,12 +333,14 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
       GemmOperands g = {ws.mul_L + nn, N, 0, Bm, N, 0, nullptr, N, N, N, ks};
       EpiPartial epi = {ws.skbuf, N, (long long)nn};
       SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb_splitk")));
-      splitk_reduce_kernel<<<ceil_div((int)nn, 256), 256, 0, st>>>(ws.skbuf, ks, (int)nn, 2.f, Cin, -1.f, Cm);
+      splitk_reduce_kernel<<<ceil_div((int)nn, 256), 256, 0, st>>>(ws.skbuf, ks, (int)nn, 2.f, Cin, -1.f, Cm,
+                                                                    ws.mul_Lp + (size_t)(term - 1) * N * Np, N, Np);
       SG_LAUNCH_CHECK("splitk_reduce_kernel");
     } else {
       GemmOperands g = {ws.mul_L + nn, N, 0, Bm, N, 0, nullptr, N, N, N};
       EpiAxpby epi = {Cm, N, 0, Cin, N, 0, 2.f, Cin != nullptr ? -1.f : 0.f};
       SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb")));
+      SG_TRY(launch_pad_rows(Cm, N, N, N, ws.mul_Lp + (size_t)(term - 1) * N * Np, Np, st));
     }
   }
   return 0;
@@ -355,16 +392,17 @@ int stemgnn_model_forward(const stemgnn_dims_t* dims, const stemgnn_params_t* p,
   const stemgnn_dims_t& dm = *dims;
   Workspace ws = carve_workspace(dm, opts->training, static_cast<float*>(workspace));
 
-  SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dm.B, dm.W, dm.N, st));
+  SG_TRY(launch_prep_layouts(x, ws.xs, ws.x_bnw, dm.B, dm.W, dm.N, st, ws.x_pad, pad4(dm.N)));
   GruArgs ga = {ws.xs, p->gru_w_ih, p->gru_w_hh, p->gru_b_ih, p->gru_b_hh, p->weight_key,
                 p->weight_query, ws.key, ws.query, ws.h_all, ws.gi, ws.g_r, ws.g_z, ws.g_n, ws.g_hn, dm.B, dm.N, dm.W};
   ga.tc_reuse = (opts->reuse_folded && !opts->training) ? 1 : 0;
   SG_TRY(gru_keyquery_forward(ga, 0, ws.gru_scratch, st));
   SG_TRY(graph_forward(dm, *opts, ws.key, ws.query, attention, ws, st));
   SG_TRY(block_forward(dm, p->block[0], 0, opts->gemm_mode, opts->reuse_folded && !opts->training, ws.x_bnw, x,
-                       ws.mul_L, ws.blk[0], ws.skbuf, st));
+                       ws.mul_L, ws.blk[0], ws.skbuf, st, ws.mul_Lp, ws.x_pad));
   SG_TRY(block_forward(dm, p->block[1], 1, opts->gemm_mode, opts->reuse_folded && !opts->training,
-                       ws.blk[0].bc_bnw, ws.blk[0].bc_bwn, ws.mul_L, ws.blk[1], ws.skbuf, st));
+                       ws.blk[0].bc_bnw, ws.blk[0].bc_bwn, ws.mul_L, ws.blk[1], ws.skbuf, st, ws.mul_Lp,
+                       ws.blk[0].bc_pad));
   SG_TRY(launch_model_head(ws.blk[0].forecast, ws.blk[1].forecast, p->fc0_w, p->fc0_b, p->fc2_w,
                            p->fc2_b, forecast, dm.B, dm.N, dm.W, dm.H, st));
   if (mul_L != nullptr)
@@ -434,7 +472,12 @@ int stemgnn_block_forward(const stemgnn_dims_t* dims, const stemgnn_block_params
   float* x_bwn = ws.blk[1 - stack_idx].bc_bwn;   // scratch from the other block's slot
   bnw_to_bwn_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x_bnw, x_bwn, dims->B, dims->N, dims->W);
   SG_LAUNCH_CHECK("bnw_to_bwn_kernel");
-  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, 0, x_bnw, x_bwn, mul_L, b, ws.skbuf, st));
+  // TMA-able copies of the caller's operands, so that the stage API runs the same tcgen05 kernels as the model path
+  const int Np = pad4(dims->N);
+  float* x_pad = ws.blk[1 - stack_idx].bc_pad;
+  SG_TRY(launch_pad_rows(x_bwn, (long long)dims->B * dims->W, dims->N, dims->N, x_pad, Np, st));
+  SG_TRY(launch_pad_rows(mul_L + (size_t)dims->N * dims->N, 3ll * dims->N, dims->N, dims->N, ws.mul_Lp, Np, st));
+  SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, 0, x_bnw, x_bwn, mul_L, b, ws.skbuf, st, ws.mul_Lp, x_pad));
   SG_CUDA(cudaMemcpyAsync(forecast, b.forecast, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (stack_idx == 0)
     SG_CUDA(cudaMemcpyAsync(backcast, b.bc_bnw, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -501,6 +544,31 @@ int stemgnn_sgemm(int M, int N, int K, float alpha, const float* A, int lda, int
   if (!a_kmajor && !b_nk) return launch_sgemm<false, false, false>(g, epi, 1, st, "sgemm_nn");
   if (a_kmajor && b_nk) return launch_sgemm<true, true, false>(g, epi, 1, st, "sgemm_tt");
   return launch_sgemm<true, false, false>(g, epi, 1, st, "sgemm_tn");
+}
+
+int stemgnn_tc_gemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                    int split_ops, stemgnn_stream_t stream) {
+  clear_error();
+  SG_CHECK(M > 0 && N > 0 && K > 0 && A && B && C, "tc_gemm: bad arguments");
+  const int rc = tc_gemm(M, N, K, 1.f, A, lda, B, ldb, N, C, nullptr, 0, ldc, N, 0, 1, static_cast<cudaStream_t>(stream),
+                         split_ops ? 1 : 0);
+  SG_CHECK(rc >= 0, "tc_gemm: unsupported shape M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
+  return rc;
+}
+
+int stemgnn_gft_forward(const float* mul_L, const float* x, float* G, int B, int N, int W, float* scratch,
+                        stemgnn_stream_t stream) {
+  clear_error();
+  SG_CHECK(mul_L && x && G && scratch && B > 0 && N > 0 && W > 0, "gft_forward: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Np = pad4(N);
+  float* Lp = scratch;
+  float* xp = scratch + (size_t)4 * N * Np;
+  SG_TRY(launch_pad_rows(mul_L + (size_t)N * N, 3ll * N, N, N, Lp, Np, st));
+  SG_TRY(launch_pad_rows(x, (long long)B * W, N, N, xp, Np, st));
+  const int rc = gft_tc(Lp, Np, xp, Np, G, nullptr, 0, 0, B, N, W, 1, st);
+  SG_CHECK(rc >= 0, "gft_forward: tcgen05 path unavailable for B=%d N=%d W=%d", B, N, W);
+  return rc;
 }
 
 int stemgnn_glu_gemm(int M, int N, int K, const float* A, int lda, const float* Wl, const float* bl,

@@ -560,13 +560,14 @@ static int block_backward(const stemgnn_dims_t& dm, const stemgnn_block_params_t
           // weight gradients: [dWl; dWr] (2d x d) += dlrT (2d x R) . inT (d x R)^T   (K = R, split-K atomics)
           SG_TRY(transpose(st, in, R, d, d, w.inT, ldT));
           rc = tc_gemm(2 * d, d, R, 1.f, w.dlrT, ldT, w.inT, ldT, d, gr.glu_left_w[gidx], gr.glu_right_w[gidx], d, d,
-                       d, 1, 12, st);
+                       d, 1, 12, st, gemm_mode == 0 ? -1 : 0);
           if (rc > 0) return rc;
           if (rc == 0) {
             // input gradient: d_in (R x d) = dlr (R x 2d) . [Wl^T | Wr^T] (d x 2d)^T
             SG_TRY(transpose(st, bp.glu_left_w[gidx], d, d, d, w.wsT, 2 * d));
             SG_TRY(transpose(st, bp.glu_right_w[gidx], d, d, d, w.wsT + d, 2 * d));
-            rc = tc_gemm(R, d, 2 * d, 1.f, w.dlr, 2 * d, w.wsT, 2 * d, d, d_in, nullptr, 0, d, d, 0, 1, st);
+            rc = tc_gemm(R, d, 2 * d, 1.f, w.dlr, 2 * d, w.wsT, 2 * d, d, d_in, nullptr, 0, d, d, 0, 1, st,
+                         gemm_mode == 0 ? -1 : 0);
             if (rc > 0) return rc;
             SG_CHECK(rc == 0, "tcgen05 backward GEMM rejected after the weight-gradient GEMM ran");
           }
@@ -663,6 +664,9 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
   SG_LAUNCH_CHECK("laplacian_bwd_rows_kernel");
   laplacian_bwd_combine_kernel<<<nblocks((long long)nn, 256, 2048), 256, 0, st>>>(w.dAsym, w.ddeg, w.dA, N);
   SG_LAUNCH_CHECK("laplacian_bwd_combine_kernel");
+  // global-batch graph (forward all-reduced the shard-mean attention): the loss of EVERY rank depends on this rank's
+  // attention, so its gradient is the mean over ranks of the local d loss_k / d attention
+  if (opts->graph_allreduce != nullptr) opts->graph_allreduce(w.dA, (long long)nn, opts->graph_allreduce_user, st);
 
   // ---- softmax attention (base_model.py:156-161) ----
   AttnBwdArgs ab = {};
@@ -728,7 +732,7 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
         const int nn_ = N - n0 < 256 ? N - n0 : 256;
         const int npad = (nn_ + 15) / 16 * 16;
         rc = tc_gemm(3 * N, npad, Kr, 1.f, w.dghT, ldT, w.hT + (size_t)n0 * ldT, ldT, nn_, gr.gru_w_hh + n0, nullptr,
-                     0, N, nn_, 1, 8, st);
+                     0, N, nn_, 1, 8, st, opts->gemm_mode == 0 ? -1 : 0);
         if (rc > 0) return rc;
         // a chunk that is unsupported AFTER earlier chunks were accumulated must not fall back to the full fp32 product
         // (it would double-count the finished columns)

@@ -58,6 +58,22 @@ __device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* map, uint64
       ::"r"(su32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(su32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA load multicast to every CTA of `mask` (same CTA-relative smem offset and mbarrier in each)
+__device__ __forceinline__ void tma_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(su32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(su32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tcf_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcf_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ uint32_t elect1() {
@@ -88,6 +104,11 @@ __device__ __forceinline__ void umma_h(uint32_t d_tmem, uint64_t a_desc, uint64_
 }
 __device__ __forceinline__ void commit_h(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar)) : "memory");
+}
+__device__ __forceinline__ void commit_h_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(su32(bar)), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -144,7 +165,11 @@ struct GluHMaps {
   CUtensorMap w[3][2][2];
 };
 
-template <bool SPLIT>
+// CSZ = 2: CTA pairs (thread-block cluster of 2) share the weight ring.  Every CTA of the grid streams the SAME 1.1 MB of
+// weight images per launch, so the ring is bound by L2 -> SM bandwidth (90 CTAs x 1.1 MB); in a pair each CTA fetches half of
+// the rows of every stage and TMA-multicasts them into both CTAs' shared memory, which halves that traffic.  A stage is
+// free once BOTH CTAs have consumed it (tcgen05.commit multicast onto both empty barriers).
+template <bool SPLIT, int CSZ>
 __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_constant__ GluHMaps maps, GluHArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -175,7 +200,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < H_NSTG; ++s) {
       mb_init(&full_bar[s], 1);
-      mb_init(&empty_bar[s], 1);
+      mb_init(&empty_bar[s], CSZ);
     }
     mb_init(tmem_full_bar, 1);
     mb_init(a_ready_bar, 128);
@@ -190,8 +215,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
   }
   tcf_before();
   __syncthreads();
+  if (CSZ > 1) cluster_sync_all();      // the peer's barriers are initialised before any multicast lands
   tcf_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CSZ > 1 ? cluster_rank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CSZ) - 1u);
+  const int wrows = N / CSZ;                                    // weight rows this CTA fetches per image
+  const uint32_t woff = crank * (uint32_t)wrows * 64u;          //   and where they land inside an image of the stage
 
   if (warp == 0) {
     // ===== TMA producer (converged warp, elected lane): the input tile once, then the weight stages =====
@@ -209,12 +239,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
             mb_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* st = w_buf + (size_t)s * stage_bytes;
             mb_expect_tx(&full_bar[s], stage_bytes);
-            if (SPLIT) {
-              tma_2d(st, &maps.w[l][half][0], &full_bar[s], kb * 32, 0);
-              tma_2d(st + w_bytes, &maps.w[l][half][1], &full_bar[s], kb * 32, 0);
-            } else {
-              tma_2d(st, &maps.w[l][0][0], &full_bar[s], kb * 32, 0);
-              tma_2d(st + w_bytes, &maps.w[l][1][0], &full_bar[s], kb * 32, 0);
+            const CUtensorMap* m0p = SPLIT ? &maps.w[l][half][0] : &maps.w[l][0][0];
+            const CUtensorMap* m1p = SPLIT ? &maps.w[l][half][1] : &maps.w[l][1][0];
+            if (CSZ == 1) {
+              tma_2d(st, m0p, &full_bar[s], kb * 32, 0);
+              tma_2d(st + w_bytes, m1p, &full_bar[s], kb * 32, 0);
+            } else {          // this CTA's share of the rows, delivered to every CTA of the pair
+              tma_2d_mc(st + woff, m0p, &full_bar[s], kb * 32, (int)crank * wrows, kMask);
+              tma_2d_mc(st + w_bytes + woff, m1p, &full_bar[s], kb * 32, (int)crank * wrows, kMask);
             }
           }
         }
@@ -260,7 +292,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
                 }
               }
             }
-            commit_h(&empty_bar[s]);
+            if (CSZ == 1) commit_h(&empty_bar[s]);
+            else commit_h_mc(&empty_bar[s], kMask);     // signalled in every CTA that multicasts into this stage
           }
           __syncwarp();
         }
@@ -350,6 +383,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
     tcf_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H_TMEM_COLS) : "memory");
   }
+  if (CSZ > 1) cluster_sync_all();      // no CTA exits while its peer can still signal its barriers
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -430,14 +464,19 @@ int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const f
     for (int l = 0; l < 3; ++l)
       for (int sd = 0; sd < 2; ++sd)
         SG_TRY(conv(w[l][sd], N, l == 0 ? K1 : N, l == 0 ? K1 : N, w_img[l][sd][0], w_img[l][sd][1], kp[l]));
+  // CTA pairs with multicast weight stages unless disabled (STEMGNN_GLU_NO_MULTICAST) or half an image breaks the 8-row atom
+  static const bool no_mc = getenv("STEMGNN_GLU_NO_MULTICAST") != nullptr;
+  const int csz = (!no_mc && N % 16 == 0) ? 2 : 1;
   GluHMaps maps;
   const bool bf = !split;
-  if (!map_h(enc, &maps.g[0], g_hi, M, k1p, k1p, H_BM, 64, bf) || !map_h(enc, &maps.g[1], g_lo, M, k1p, k1p, H_BM, 64, bf))
+  // logical width K1, pitch k1p: the TMA unit zero-fills columns K1 .. k1p, so producers of the images (the tcgen05 graph
+  // Fourier transform's epilogue) need not write the padding
+  if (!map_h(enc, &maps.g[0], g_hi, M, K1, k1p, H_BM, 64, bf) || !map_h(enc, &maps.g[1], g_lo, M, K1, k1p, H_BM, 64, bf))
     return -1;
   for (int l = 0; l < 3; ++l)
     for (int sd = 0; sd < 2; ++sd)
       for (int arr = 0; arr < 2; ++arr)
-        if (!map_h(enc, &maps.w[l][sd][arr], w_img[l][sd][arr], N, kp[l], kp[l], N, 32, bf)) return -1;
+        if (!map_h(enc, &maps.w[l][sd][arr], w_img[l][sd][arr], N, kp[l], kp[l], N / csz, 32, bf)) return -1;
   const size_t smem = (size_t)(split ? 2 : 1) * 4 * H_A_CHUNK + (size_t)H_NSTG * 2 * N * 64 + 128 +
                       (size_t)6 * N * sizeof(float) + 1024;
   if (smem > 227 * 1024) return -1;
@@ -450,14 +489,38 @@ int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const f
   }
   g.out3 = out3; g.ldo3 = ldo3; g.act[0] = act[0]; g.act[1] = act[1];
   g.M = M; g.N = N; g.K1 = K1;
-  if (split) {
-    SG_CUDA(cudaFuncSetAttribute(glu_chain_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    glu_chain_h_kernel<true><<<ceil_div(M, H_BM), H_THREADS, smem, st>>>(maps, g);
-  } else {
-    SG_CUDA(cudaFuncSetAttribute(glu_chain_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    glu_chain_h_kernel<false><<<ceil_div(M, H_BM), H_THREADS, smem, st>>>(maps, g);
+  const int tiles = ceil_div(M, H_BM);
+  if (csz == 1) {
+    if (split) {
+      SG_CUDA(cudaFuncSetAttribute(glu_chain_h_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      glu_chain_h_kernel<true, 1><<<tiles, H_THREADS, smem, st>>>(maps, g);
+    } else {
+      SG_CUDA(cudaFuncSetAttribute(glu_chain_h_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      glu_chain_h_kernel<false, 1><<<tiles, H_THREADS, smem, st>>>(maps, g);
+    }
+    SG_LAUNCH_CHECK("glu_chain_h_kernel");
+    return 0;
   }
-  SG_LAUNCH_CHECK("glu_chain_h_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((tiles + 1) / 2 * 2);       // an odd tail tile gets a partner whose rows are all out of range
+  cfg.blockDim = dim3(H_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (split) {
+    SG_CUDA(cudaFuncSetAttribute(glu_chain_h_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaLaunchKernelEx(&cfg, glu_chain_h_kernel<true, 2>, maps, g));
+  } else {
+    SG_CUDA(cudaFuncSetAttribute(glu_chain_h_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CUDA(cudaLaunchKernelEx(&cfg, glu_chain_h_kernel<false, 2>, maps, g));
+  }
+  count_launch();
   return 0;
 }
 

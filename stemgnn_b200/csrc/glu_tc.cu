@@ -685,9 +685,18 @@ int glu_gemm_tc(int M, int N, int K, const float* A, int lda, const float* Wl, c
 }
 
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
-            float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st) {
+            float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st,
+            int split_ops) {
   if (N % 16 != 0 || N < 16 || N > 256 || K < 1 || (lda & 3) != 0 || (ldb & 3) != 0) return -1;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
+  // default: 3xTF32 split operands (spec_tc.cu; fp32-level results).  STEMGNN_TC_NOSPLIT=1 keeps the round-1 single
+  // truncated-TF32 pass below (3x fewer MMAs, ~2^-10 operand error) for A/B measurements.
+  static const bool nosplit = getenv("STEMGNN_TC_NOSPLIT") != nullptr;
+  if (split_ops < 0) split_ops = nosplit ? 0 : 1;
+  if (split_ops) {
+    const int rc = tc3_gemm(M, N, K, alpha, A, lda, B, ldb, n_rows_b, C0, C1, msplit, ldc, n_store, atomic, splits, 1, st);
+    if (rc >= 0) return rc;
+  }
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return -1;
   CUtensorMap ma, mb;

@@ -52,10 +52,13 @@ struct AttnArgs {
   int use_dropout;       // 0: eval
   int B, N;
 };
-int launch_prep_layouts(const float* x, float* xs, float* x_bnw, int B, int W, int N, cudaStream_t st);
+// x_pad (optional): (B*W, ld_pad) copy of x with a TMA-able row pitch (ld_pad % 4 == 0), operand of the tcgen05 GFT
+int launch_prep_layouts(const float* x, float* xs, float* x_bnw, int B, int W, int N, cudaStream_t st,
+                        float* x_pad = nullptr, int ld_pad = 0);
 int launch_attention(const AttnArgs& a, float* qmax, cudaStream_t st);
+// L_pad (optional): (N, ld_pad) copy of mul_L[1]
 int launch_laplacian(const float* a_raw, const float* deg, float* attention, float* mul_L, int N,
-                     cudaStream_t st);
+                     cudaStream_t st, float* L_pad = nullptr, int ld_pad = 0);
 
 // ---- fused Laplacian + Jacobi eigensolver (eig.cu), opt-in graph mode ---------------------------------------------------
 int laplacian_eig(const float* a_raw, const float* deg, int N, float* lambda, float* U, int* info, int max_sweeps,
@@ -104,9 +107,21 @@ int glu_chain_h(int mode, int M, int N, int K1, const float* G, int ldg, const f
                 float* const save_s[3], unsigned short* scratch, int reuse_w, const unsigned short* g_shared,
                 cudaStream_t st, int g_ready = 0);
 
-// generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1
+// generic tcgen05 TF32 GEMM (glu_tc.cu): C0/C1 (+)= alpha A[M,K] B[N,K]^T; rows m >= msplit go to C1.
+// split_ops: 1 = 3xTF32 split operands (spec_tc.cu, fp32-level), 0 = one truncated-TF32 pass, -1 = default (split unless
+// STEMGNN_TC_NOSPLIT is set)
 int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b,
-            float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st);
+            float* C0, float* C1, int msplit, int ldc, int n_store, int atomic, int splits, cudaStream_t st,
+            int split_ops = -1);
+
+// ---- spectral-block GEMMs on tcgen05 with 3xTF32 split operands (spec_tc.cu): 0 ok, -1 unsupported, >0 error -------------
+int launch_pad_rows(const float* src, long long rows, int cols, int ld_src, float* dst, int ld_dst, cudaStream_t st);
+int tc3_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b, float* C0,
+             float* C1, int msplit, int ldc, int n_store, int atomic, int splits, int split_ops, cudaStream_t st);
+int gft_tc(const float* mul_Lp, int ldl, const float* xp, int ldx, float* G, unsigned short* g_img, int ldh, int bf16,
+           int B, int N, int W, int split_ops, cudaStream_t st);
+int out_head_tc(const float* act3, int K, const float* woutT, int PWp, const HeadArgs& h, float* bc_pad, int ld_pad,
+                int split_ops, cudaStream_t st);
 
 // ---- workspace ---------------------------------------------------------------------------------------
 struct BlockWs {
@@ -122,6 +137,7 @@ struct BlockWs {
   float* forecast; // (R, W)
   float* bc_bnw;   // (R, W) backcast, block-input layout
   float* bc_bwn;   // (B, W, N) backcast, GFT operand layout
+  float* bc_pad;   // (B*W, pad4(N)) the same with a TMA-able row pitch (operand of the tcgen05 GFT of the next block)
   float* save_l[6]; float* save_s[6];   // training: GLU left pre-activation / gate per GLU index
   float* fs;       // training: forecast_source (R, T)
   float* hscratch[2];   // per chain: 16-bit operand images of the kind::f16 GLU chain (G hi/lo + weight hi/lo)
@@ -138,6 +154,7 @@ struct BwdWs {
 struct Workspace {
   float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
   float* skbuf;    // split-K partial products (8 x max(N*N, 3N*B*W) floats)
+  float *mul_Lp, *x_pad;   // (3N, pad4(N)) = mul_L[1..3] and (B*W, pad4(N)) = x with TMA-able row pitches
   float *row_m, *row_zinv, *h_all, *g_r, *g_z, *g_n, *g_hn;
   float *eig_lambda, *eig_U, *eig_S;   // eig graph mode: eigenvalues (n), eigenvectors (n,n), scaled copy (N,n)
   int* eig_info;

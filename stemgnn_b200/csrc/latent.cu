@@ -13,7 +13,8 @@ namespace sg {
 
 // x (B,W,N) -> xs (N,B,W) [GRU sequence layout] and x_bnw (B,N,W) [spectral-block layout]
 __global__ void prep_layouts_kernel(const float* __restrict__ x, float* __restrict__ xs,
-                                    float* __restrict__ x_bnw, int B, int W, int N) {
+                                    float* __restrict__ x_bnw, int B, int W, int N, float* __restrict__ x_pad,
+                                    int ld_pad) {
   const long long total = (long long)B * W * N;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -23,25 +24,9 @@ __global__ void prep_layouts_kernel(const float* __restrict__ x, float* __restri
     const float v = x[idx];
     xs[((long long)n * B + b) * W + t] = v;
     x_bnw[((long long)b * N + n) * W + t] = v;
+    if (x_pad != nullptr) x_pad[((long long)b * W + t) * ld_pad + n] = v;
   }
 }
-
-// qmax[b] = max_j query[b,j]
-__global__ void row_max_kernel(const float* __restrict__ q, float* __restrict__ qmax, int N) {
-  __shared__ float red[32];
-  const int b = blockIdx.x;
-  float m = -INFINITY;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) m = fmaxf(m, q[(long long)b * N + j]);
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float r = threadIdx.x < ((blockDim.x + 31) >> 5) ? red[threadIdx.x] : -INFINITY;
-    r = warp_max(r);
-    if (threadIdx.x == 0) qmax[b] = r;
-  }
-}
-
 
 // one CTA per attention row i
 __global__ void __launch_bounds__(256) attention_mean_kernel(AttnArgs a) {
@@ -58,7 +43,12 @@ __global__ void __launch_bounds__(256) attention_mean_kernel(AttnArgs a) {
   // phase 1: one warp per batch element: softmax denominator of row (b,i)
   for (int b = wid; b < B; b += nw) {
     const float ki = s_key[b];
-    const float m = leaky_(ki + a.qmax[b], a.alpha);
+    // row maximum without materialising the row: max_j lrelu(k_i + q_j) = lrelu(k_i + max_j q_j) (file header); the query row
+    // is read twice from L1/L2 by the same warp instead of once more by a separate kernel launch
+    float qm = -INFINITY;
+    for (int j = lane; j < N; j += 32) qm = fmaxf(qm, a.query[(long long)b * N + j]);
+    qm = warp_max(qm);
+    const float m = leaky_(ki + qm, a.alpha);
     float z = 0.f;
     for (int j = lane; j < N; j += 32)
       z += expf(leaky_(ki + a.query[(long long)b * N + j], a.alpha) - m);
@@ -98,7 +88,8 @@ __global__ void __launch_bounds__(256) attention_mean_kernel(AttnArgs a) {
 
 // attention_sym = (A + A^T)/2 ;  L = D^ (diag(deg) - attention_sym) D^ ;  mul_L[0] = 0, mul_L[1] = L
 __global__ void laplacian_kernel(const float* __restrict__ a_raw, const float* __restrict__ deg,
-                                 float* __restrict__ attention, float* __restrict__ mul_L, int N) {
+                                 float* __restrict__ attention, float* __restrict__ mul_L, int N,
+                                 float* __restrict__ L_pad, int ld_pad) {
   const long long total = (long long)N * N;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -109,21 +100,23 @@ __global__ void laplacian_kernel(const float* __restrict__ a_raw, const float* _
     const float inner = ((i == j) ? deg[i] : 0.f) - asym;
     attention[idx] = asym;
     mul_L[idx] = 0.f;
-    mul_L[total + idx] = di * (inner * dj);
+    const float l = di * (inner * dj);
+    mul_L[total + idx] = l;
+    if (L_pad != nullptr) L_pad[(long long)i * ld_pad + j] = l;
   }
 }
 
-int launch_prep_layouts(const float* x, float* xs, float* x_bnw, int B, int W, int N, cudaStream_t st) {
+int launch_prep_layouts(const float* x, float* xs, float* x_bnw, int B, int W, int N, cudaStream_t st, float* x_pad,
+                        int ld_pad) {
   const long long total = (long long)B * W * N;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  prep_layouts_kernel<<<blocks, 256, 0, st>>>(x, xs, x_bnw, B, W, N);
+  prep_layouts_kernel<<<blocks, 256, 0, st>>>(x, xs, x_bnw, B, W, N, x_pad, ld_pad);
   SG_LAUNCH_CHECK("prep_layouts_kernel");
   return 0;
 }
 
 int launch_attention(const AttnArgs& a, float* qmax, cudaStream_t st) {
-  row_max_kernel<<<a.B, 128, 0, st>>>(a.query, qmax, a.N);
-  SG_LAUNCH_CHECK("row_max_kernel");
+  (void)qmax;      // (round 1 launched a separate row-max kernel into this buffer; the attention kernel computes it now)
   const size_t smem = (size_t)3 * a.B * sizeof(float);
   SG_CHECK(smem <= 40 * 1024, "attention: batch %d too large for the row kernel", a.B);
   attention_mean_kernel<<<a.N, 256, smem, st>>>(a);
@@ -132,10 +125,10 @@ int launch_attention(const AttnArgs& a, float* qmax, cudaStream_t st) {
 }
 
 int launch_laplacian(const float* a_raw, const float* deg, float* attention, float* mul_L, int N,
-                     cudaStream_t st) {
+                     cudaStream_t st, float* L_pad, int ld_pad) {
   const long long total = (long long)N * N;
   const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  laplacian_kernel<<<blocks, 256, 0, st>>>(a_raw, deg, attention, mul_L, N);
+  laplacian_kernel<<<blocks, 256, 0, st>>>(a_raw, deg, attention, mul_L, N, L_pad, ld_pad);
   SG_LAUNCH_CHECK("laplacian_kernel");
   return 0;
 }

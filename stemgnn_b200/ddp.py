@@ -8,9 +8,14 @@ last backward kernel — see `runtime.StemGNNFunction.backward`.  Parameters tha
 gradient (`stock_block.1.backcast_short_cut.*`, base_model.py:70-74) are zeros in the buffer on every
 rank, so no `find_unused_parameters` machinery is needed.
 
-Graph semantics: each replica builds the latent graph from ITS shard of the batch
+Graph semantics: by default each replica builds the latent graph from ITS shard of the batch
 (`torch.mean(attention, dim=0)`, base_model.py:140) — standard DDP semantics, not identical to one
-process with the global batch (documented in DESIGN.md §multi-GPU).
+process with the global batch.  `attach(model, global_graph=True)` restores the global-batch semantics
+with a second, small exchange: the batch-mean attention (N x N) and its degree vector are all-reduced in
+the forward before the Laplacian is formed, and the gradient with respect to that attention is
+all-reduced in the backward (`stemgnn_fwd_opts_t.graph_allreduce`, `runtime.GraphAllreduce`).  With
+equal shards an N-rank step then equals the single-process step on the concatenated batch (up to fp32
+summation order) — `tests/ddp_global_graph_check.py`.
 """
 import os
 
@@ -57,11 +62,13 @@ def broadcast_parameters(module, src=0, group=None):
             module.invalidate_runtime()                      # folded / pre-split weight caches are stale now
 
 
-def attach(model, group=None):
+def attach(model, group=None, global_graph=False):
     """Marks a stemgnn_b200 Model for data-parallel training: its backward all-reduces the flat
-    gradient buffer before handing gradients to autograd."""
+    gradient buffer before handing gradients to autograd.  global_graph=True additionally exchanges the
+    batch-mean attention so that every replica uses the graph of the GLOBAL batch (module docstring)."""
     ws = world_size(group)
-    model._ddp = {"group": group, "enabled": ws > 1, "rank": dist.get_rank(group) if ws > 1 else 0}
+    model._ddp = {"group": group, "enabled": ws > 1, "rank": dist.get_rank(group) if ws > 1 else 0,
+                  "global_graph": bool(global_graph) and ws > 1}
     broadcast_parameters(model, 0, group)
     return model
 

@@ -113,6 +113,38 @@ def make_opts(alpha, p, training, seed=0, offset=0, mask=None, gemm_mode=GEMM_AU
     return o
 
 
+class GraphAllreduce:
+    """`stemgnn_fwd_opts_t.graph_allreduce` for data-parallel runs with GLOBAL-batch graph semantics: the library calls back
+    (on the host, while it issues its launches) with a device buffer inside `workspace`; the buffer is replaced by its mean over
+    the ranks with one `torch.distributed.all_reduce` enqueued on the current stream.  ctypes swallows exceptions raised in
+    callbacks, so they are parked here and re-raised by `check()` after the C call returned."""
+
+    def __init__(self, workspace, group=None):
+        self.ws, self.group, self.error, self.calls = workspace, group, None, 0
+        self.fn = _lib.ALLREDUCE_FN(self._cb)       # keep the trampoline alive as long as this object
+
+    def _cb(self, ptr, n, _user, _stream):
+        try:
+            from . import ddp
+            off = int(ptr) - self.ws.data_ptr()
+            if off < 0 or off + 4 * n > self.ws.numel():
+                raise RuntimeError("graph_allreduce: buffer outside the workspace")
+            ddp.allreduce_mean_(self.ws[off:off + 4 * n].view(torch.float32), self.group)
+            self.calls += 1
+        except BaseException as exc:                 # noqa: BLE001 - re-raised in check()
+            self.error = exc
+
+    def install(self, opts):
+        opts.graph_allreduce = self.fn
+        opts.graph_allreduce_user = None
+        return self
+
+    def check(self):
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise RuntimeError("stemgnn_b200: graph all-reduce failed") from err
+
+
 def model_forward_raw(dims, ptrs, opts, x, workspace, want_mul_L=False):
     """One call of stemgnn_model_forward on the current stream.  Returns (forecast, attention, mul_L)."""
     lib = _lib.load()
@@ -141,7 +173,13 @@ class StemGNNFunction(torch.autograd.Function):
         opts = make_opts(alpha, p_drop if use_dropout else 0.0, True, seed, offset,
                          mask if use_dropout else None, gemm_mode)
         ws = alloc_workspace(dims, True, x.device)
+        ddp_state = cfg[8] if len(cfg) > 8 else None
+        ctx.graph_ar = None
+        if ddp_state is not None and ddp_state.get("global_graph"):
+            ctx.graph_ar = GraphAllreduce(ws, ddp_state.get("group")).install(opts)
         forecast, attention, _ = model_forward_raw(dims, ptrs, opts, x, ws)
+        if ctx.graph_ar is not None:
+            ctx.graph_ar.check()
         ctx.save_for_backward(x, *params)
         ctx.cfg = cfg
         ctx.ws = ws
@@ -177,6 +215,9 @@ class StemGNNFunction(torch.autograd.Function):
                                         byref(gptrs), d_x.data_ptr() if need_dx else None,
                                         ctx.ws.data_ptr(), ctx.ws.numel(), _stream_ptr(dev))
         _lib.check(rc, "stemgnn_model_backward")
+        if ctx.graph_ar is not None:
+            ctx.graph_ar.check()
+            ctx.graph_ar = None
         ctx.ws = None
         ddp_group = ctx.cfg[8] if len(ctx.cfg) > 8 else None
         if ddp_group is not None:                 # the ONE collective of a training step

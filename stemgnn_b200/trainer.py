@@ -124,13 +124,18 @@ class FusedTrainer:
         opts = runtime.make_opts(m.alpha, m.dropout_rate if use_dropout else 0.0, True, seed=self.seed, offset=0,
                                  gemm_mode=m.gemm_mode)
         opts.dropout_offset_dev = self.drop_dev.data_ptr()
-        return {"dims": dims, "opts": opts,
+        ws = runtime.alloc_workspace(dims, True, dev)
+        ddp_state = getattr(m, "_ddp", None) or {}
+        graph_ar = None
+        if ddp_state.get("enabled") and ddp_state.get("global_graph"):    # global-batch graph: 2 small all-reduces (ddp.py)
+            graph_ar = runtime.GraphAllreduce(ws, ddp_state.get("group")).install(opts)
+        return {"dims": dims, "opts": opts, "graph_ar": graph_ar,
                 "x": torch.empty(B, m.time_step, m.unit, dtype=torch.float32, device=dev),
                 "y": torch.empty(B, m.horizon, m.unit, dtype=torch.float32, device=dev),
                 "forecast": torch.empty(B, m.horizon, m.unit, dtype=torch.float32, device=dev),
                 "attention": torch.empty(m.unit, m.unit, dtype=torch.float32, device=dev),
                 "d_forecast": torch.empty(B, m.horizon, m.unit, dtype=torch.float32, device=dev),
-                "ws": runtime.alloc_workspace(dims, True, dev), "graph": None, "calls": 0,
+                "ws": ws, "graph": None, "calls": 0,
                 "drop_inc": (B * m.unit * m.unit + 3) // 4 + 1}
 
     def _body(self, s):
@@ -149,6 +154,8 @@ class FusedTrainer:
                                         s["d_forecast"].data_ptr(), None, byref(self.gptrs), None,
                                         s["ws"].data_ptr(), s["ws"].numel(), st)
         _lib.check(rc, "stemgnn_model_backward")
+        if s["graph_ar"] is not None:
+            s["graph_ar"].check()
         ddp_state = getattr(m, "_ddp", None)
         if ddp_state and ddp_state.get("enabled"):          # the ONE collective of a training step
             from . import ddp

@@ -49,7 +49,9 @@ def test_backward_vs_reference_gradient_golden(name, mode):
         gen = torch.Generator().manual_seed(99)
         mask = (torch.rand(c["B"], c["N"], c["N"], generator=gen) >= c["p_drop"])
     m, xd, forecast, loss = _run(c, mask, {"fp32": runtime.GEMM_FP32, "tc": runtime.GEMM_TC, "auto": runtime.GEMM_AUTO}[mode])
-    rtol = 2e-3 if mode == "fp32" else 1e-2
+    # default mode: every tensor-core GEMM of the backward runs on 3xTF32 split operands (csrc/spec_tc.cu), so it meets the
+    # exact-fp32 bound; only the explicit round-1 mode (one truncated-TF32 pass) needs the loose one
+    rtol = 1e-2 if mode == "tc" else 2e-3
     assert abs(loss - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
     assert_close(forecast, g["forecast"], msg="forecast")
     _rel_check("grad.x", xd.grad, g["grad.x"], rtol)

@@ -182,7 +182,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.stemgnn_version() == 2
+    assert lib.stemgnn_version() == _lib.ABI_VERSION == 3
     d = _lib.Dims(32, 358, 12, 3, 5)
     import ctypes
     ev, tr = lib.stemgnn_workspace_bytes(ctypes.byref(d), 0), lib.stemgnn_workspace_bytes(ctypes.byref(d), 1)
