@@ -292,7 +292,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ P, int ks, int n,
   for (int z = 0; z < ks; ++z) acc += P[(long long)z * n + i];
   const float v = alpha * acc + (Cin != nullptr ? beta * Cin[i] : 0.f);
   C[i] = v;
-  if (C2 != nullptr) C2[(long long)(i / ncols) * ld2 + i % ncols] = v;
+  if (C2 != nullptr) C2[(long long)(i / ncols) * ld2 + i % ncols] = v;      // ld2 may carry a row interleave (3 * pitch)
 }
 
 int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const float* key,
@@ -312,7 +312,8 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
     op.graph_allreduce(ws.a_raw, (long long)N * N, op.graph_allreduce_user, st);
     op.graph_allreduce(ws.deg, N, op.graph_allreduce_user, st);
   }
-  const int Np = pad4(N);      // ws.mul_Lp: (3N, Np) copy of mul_L[1..3] for the tcgen05 graph Fourier transform
+  // ws.mul_Lp: (3N, Np) copy of mul_L[1..3] for the tcgen05 graph Fourier transform, rows interleaved as n*3 + k'
+  const int Np = pad4(N);
   SG_TRY(launch_laplacian(ws.a_raw, ws.deg, attention, ws.mul_L, N, st, ws.mul_Lp, Np));
   const size_t nn = (size_t)N * N;
   if (op.graph_mode == 1 && !op.training && N >= 2 && N <= 512) {
@@ -320,7 +321,7 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
     // Laplacian + Jacobi kernel, polynomial stack rebuilt as U p(Lambda) U^T
     SG_TRY(laplacian_eig(ws.a_raw, ws.deg, N, ws.eig_lambda, ws.eig_U, ws.eig_info, 30, 1e-6f, st));
     SG_TRY(eig_poly_stack(ws.eig_lambda, ws.eig_U, N, ws.eig_S, ws.mul_L, st));
-    return launch_pad_rows(ws.mul_L + nn, 3ll * N, N, N, ws.mul_Lp, Np, st);
+    return launch_pad_rows(ws.mul_L + nn, 3ll * N, N, N, ws.mul_Lp, Np, st, 3, 0, N);
   }
   // the two N^3 Chebyshev products fill only a few CTAs: deterministic split-K (partials + ordered reduce)
   const int ks = pick_ksplit(N, N, N);
@@ -334,13 +335,13 @@ int graph_forward(const stemgnn_dims_t& dm, const stemgnn_fwd_opts_t& op, const 
       EpiPartial epi = {ws.skbuf, N, (long long)nn};
       SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb_splitk")));
       splitk_reduce_kernel<<<ceil_div((int)nn, 256), 256, 0, st>>>(ws.skbuf, ks, (int)nn, 2.f, Cin, -1.f, Cm,
-                                                                    ws.mul_Lp + (size_t)(term - 1) * N * Np, N, Np);
+                                                                    ws.mul_Lp + (size_t)(term - 1) * Np, N, 3 * Np);
       SG_LAUNCH_CHECK("splitk_reduce_kernel");
     } else {
       GemmOperands g = {ws.mul_L + nn, N, 0, Bm, N, 0, nullptr, N, N, N};
       EpiAxpby epi = {Cm, N, 0, Cin, N, 0, 2.f, Cin != nullptr ? -1.f : 0.f};
       SG_TRY((launch_sgemm<false, false, false>(g, epi, 1, st, "cheb")));
-      SG_TRY(launch_pad_rows(Cm, N, N, N, ws.mul_Lp + (size_t)(term - 1) * N * Np, Np, st));
+      SG_TRY(launch_pad_rows(Cm, N, N, N, ws.mul_Lp, Np, st, 3, term - 1));
     }
   }
   return 0;
@@ -476,7 +477,8 @@ int stemgnn_block_forward(const stemgnn_dims_t* dims, const stemgnn_block_params
   const int Np = pad4(dims->N);
   float* x_pad = ws.blk[1 - stack_idx].bc_pad;
   SG_TRY(launch_pad_rows(x_bwn, (long long)dims->B * dims->W, dims->N, dims->N, x_pad, Np, st));
-  SG_TRY(launch_pad_rows(mul_L + (size_t)dims->N * dims->N, 3ll * dims->N, dims->N, dims->N, ws.mul_Lp, Np, st));
+  SG_TRY(launch_pad_rows(mul_L + (size_t)dims->N * dims->N, 3ll * dims->N, dims->N, dims->N, ws.mul_Lp, Np, st, 3, 0,
+                         dims->N));
   SG_TRY(block_forward(*dims, *bp, stack_idx, gemm_mode, 0, x_bnw, x_bwn, mul_L, b, ws.skbuf, st, ws.mul_Lp, x_pad));
   SG_CUDA(cudaMemcpyAsync(forecast, b.forecast, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (stack_idx == 0)
@@ -564,7 +566,7 @@ int stemgnn_gft_forward(const float* mul_L, const float* x, float* G, int B, int
   const int Np = pad4(N);
   float* Lp = scratch;
   float* xp = scratch + (size_t)4 * N * Np;
-  SG_TRY(launch_pad_rows(mul_L + (size_t)N * N, 3ll * N, N, N, Lp, Np, st));
+  SG_TRY(launch_pad_rows(mul_L + (size_t)N * N, 3ll * N, N, N, Lp, Np, st, 3, 0, N));
   SG_TRY(launch_pad_rows(x, (long long)B * W, N, N, xp, Np, st));
   const int rc = gft_tc(Lp, Np, xp, Np, G, nullptr, 0, 0, B, N, W, 1, st);
   SG_CHECK(rc >= 0, "gft_forward: tcgen05 path unavailable for B=%d N=%d W=%d", B, N, W);

@@ -25,7 +25,9 @@ namespace sg {
 namespace {
 
 constexpr int H_BM = 128;
-constexpr int H_THREADS = 192;          // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2..5: epilogue
+constexpr int H_THREADS = 320;          // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2..9: epilogue
+constexpr int H_EPI = 256;              // (ncu: the three serial epilogues were ~half of the kernel with ONE warp per scheduler;
+                                        //  the two warps that share a TMEM lane quarter now split the columns)
 constexpr int H_RIGHT_COL = 256;
 constexpr uint32_t H_TMEM_COLS = 512;
 constexpr int H_NSTG = 3;
@@ -172,7 +174,9 @@ struct GluHMaps {
 template <bool SPLIT, int CSZ>
 __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_constant__ GluHMaps maps, GluHArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array: an integer round trip would demote the epilogue's
+  // shared-memory accesses to generic LD/ST (seen in the ncu source view)
+  uint8_t* smem = smem_raw + ((1024u - (su32(smem_raw) & 1023u)) & 1023u);
   constexpr int NARR = SPLIT ? 2 : 1;
   const int N = g.N;
   const uint32_t w_bytes = (uint32_t)N * 64;            // N rows x 32 halves
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
       mb_init(&empty_bar[s], CSZ);
     }
     mb_init(tmem_full_bar, 1);
-    mb_init(a_ready_bar, 128);
+    mb_init(a_ready_bar, H_EPI);
     mb_init(g_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -302,14 +306,17 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warps 2..5 =====
-    for (int i = threadIdx.x - 64; i < 3 * N; i += 128) {
+    // ===== epilogue: warps 2..9 =====
+    for (int i = threadIdx.x - 64; i < 3 * N; i += H_EPI) {
       const int l = i / N, c = i - l * N;
       s_bias[(l * 2 + 0) * N + c] = __ldg(g.bl[l] + c);
       s_bias[(l * 2 + 1) * N + c] = __ldg(g.br[l] + c);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                      // column half of this warp
+    const int c_split = ((N / 16 + 1) / 2) * 16;
+    const int c_begin = half ? c_split : 0, c_end = half ? N : c_split;
     const int rloc = quarter * 32 + lane;
     const int row = m0 + rloc;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
       const float* sbr = s_bias + (l * 2 + 1) * N;
       float* gout = l == 2 ? g.out3 : g.act[l];
       const int ldo = l == 2 ? g.ldo3 : N;
-      for (int c = 0; c < N; c += 16) {
+      for (int c = c_begin; c < c_end; c += 16) {
         float lv[16], rv[16], o[16];
         ld16(taddr + c, lv);
         ld16(taddr + H_RIGHT_COL + c, rv);

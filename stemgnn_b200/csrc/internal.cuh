@@ -56,7 +56,7 @@ struct AttnArgs {
 int launch_prep_layouts(const float* x, float* xs, float* x_bnw, int B, int W, int N, cudaStream_t st,
                         float* x_pad = nullptr, int ld_pad = 0);
 int launch_attention(const AttnArgs& a, float* qmax, cudaStream_t st);
-// L_pad (optional): (N, ld_pad) copy of mul_L[1]
+// L_pad (optional): row i of mul_L[1] is also written to row 3*i of L_pad (pitch ld_pad): interleaved Chebyshev stack
 int launch_laplacian(const float* a_raw, const float* deg, float* attention, float* mul_L, int N,
                      cudaStream_t st, float* L_pad = nullptr, int ld_pad = 0);
 
@@ -115,7 +115,10 @@ int tc_gemm(int M, int N, int K, float alpha, const float* A, int lda, const flo
             int split_ops = -1);
 
 // ---- spectral-block GEMMs on tcgen05 with 3xTF32 split operands (spec_tc.cu): 0 ok, -1 unsupported, >0 error -------------
-int launch_pad_rows(const float* src, long long rows, int cols, int ld_src, float* dst, int ld_dst, cudaStream_t st);
+// padded (TMA-able) copy with an optional row permutation (spec_tc.cu); row_mul = 3, stack_n = N: the three stacked Chebyshev
+// terms interleaved as row n*3 + k'
+int launch_pad_rows(const float* src, long long rows, int cols, int ld_src, float* dst, int ld_dst, cudaStream_t st,
+                    int row_mul = 1, int row_add = 0, int stack_n = 0);
 int tc3_gemm(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, int n_rows_b, float* C0,
              float* C1, int msplit, int ldc, int n_store, int atomic, int splits, int split_ops, cudaStream_t st);
 int gft_tc(const float* mul_Lp, int ldl, const float* xp, int ldx, float* G, unsigned short* g_img, int ldh, int bf16,
@@ -154,7 +157,7 @@ struct BwdWs {
 struct Workspace {
   float *xs, *x_bnw, *key, *query, *qmax, *a_raw, *deg, *mul_L, *attention, *gru_scratch, *gi;
   float* skbuf;    // split-K partial products (8 x max(N*N, 3N*B*W) floats)
-  float *mul_Lp, *x_pad;   // (3N, pad4(N)) = mul_L[1..3] and (B*W, pad4(N)) = x with TMA-able row pitches
+  float *mul_Lp, *x_pad;   // (3N, pad4(N)): row n*3 + k' = mul_L[k'+1][n][:], and (B*W, pad4(N)) = x; TMA-able row pitches
   float *row_m, *row_zinv, *h_all, *g_r, *g_z, *g_n, *g_hn;
   float *eig_lambda, *eig_U, *eig_S;   // eig graph mode: eigenvalues (n), eigenvectors (n,n), scaled copy (N,n)
   int* eig_info;

@@ -102,7 +102,7 @@ __global__ void laplacian_kernel(const float* __restrict__ a_raw, const float* _
     mul_L[idx] = 0.f;
     const float l = di * (inner * dj);
     mul_L[total + idx] = l;
-    if (L_pad != nullptr) L_pad[(long long)i * ld_pad + j] = l;
+    if (L_pad != nullptr) L_pad[(long long)(3 * i) * ld_pad + j] = l;    // row i*3 + k', k' = 0
   }
 }
 

@@ -15,12 +15,18 @@
 // accumulator — and the cross terms are 2^-10 of the main product, so in their own accumulator they are truncated at
 // 2^-34 instead of adding two more 2^-24 truncations per K step to the main sum.)
 //
-// Pipeline per 32-column K block (one 128-byte swizzle row):
+// Pipeline per 32-column K block (one 128-byte swizzle row), 320 threads:
 //   warp 0        TMA producer: fp32 tiles of A (128 rows) and B (NT rows), 128B-swizzled, K tail / row tail zero-filled
-//   warps 2..5    converters: mask the tile in place to `hi`, write `lo` to a second tile of the same (swizzled) layout —
+//   warps 2..9    converters: mask the tile in place to `hi`, write `lo` to a second tile of the same (swizzled) layout —
 //                 the transform is elementwise, so it is layout agnostic — fence.proxy.async, arrive on conv_bar
-//   warp 1        converged warp, elected lane issues 3 tcgen05.mma per K step; tcgen05.commit frees the stage
-//   warps 2..5    epilogue from tensor memory (tcgen05.ld 32x32b: thread = accumulator row)
+//   warp 1        converged warp, elected lane issues the tcgen05.mma of a K step; tcgen05.commit frees the stage.
+//                 Stage layout [A_hi | A_lo | B_hi | B_lo]: when 2*NT <= 256 the B operand of the first MMA is the STACKED
+//                 tile [B_hi; B_lo] (N = 2*NT), so A_hi is read once for hi.hi (columns [0,NT)) and hi.lo (columns [NT,2NT));
+//                 the second MMA adds lo.hi onto the cross-term columns: 2 instructions per K step instead of 3.
+//   warps 2..9    epilogue from tensor memory (tcgen05.ld 32x32b: thread = accumulator row; the two warps that share a
+//                 TMEM lane quarter split the columns).  ncu (profiles/r02_ncu_spec_*): these kernels are bound by
+//                 shared-memory bandwidth (TMA fill + split traffic + 3x operand reads) and by the epilogue's latency
+//                 chains, not by the tensor pipe — hence 8 worker warps and the stacked B operand.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -34,7 +40,8 @@ namespace {
 
 constexpr int S_BM = 128;
 constexpr int S_BK = 32;                 // fp32 elements per K block = one 128-byte swizzle row
-constexpr int S_THREADS = 192;
+constexpr int S_THREADS = 320;          // warp 0 TMA, warp 1 MMA issue, warps 2..9 operand split + epilogue
+constexpr int S_WORKERS = 256;
 constexpr uint32_t S_A_BYTES = S_BM * 128;
 
 enum { EPI_STORE = 0, EPI_GFT = 1, EPI_HEAD = 2 };
@@ -118,11 +125,13 @@ struct Tc3Args {
   int NT;              // columns (rows of the B operand) per CTA: multiple of 16, 16..256
   int nstage;          // smem ring depth
   int split;           // 1: 3xTF32 split products (fp32 parity), 0: one product on the raw fp32 bits
-  uint32_t tmem_cols;  // allocation: power of two >= max(32, NT), doubled with split operands (second accumulator)
-  uint32_t lo_col;     // column offset of the cross-term accumulator (split only)
+  int stacked;         // split only: [B_hi; B_lo] used as ONE B operand of N = 2*NT (needs 2*NT <= 256)
+  uint32_t tmem_cols;  // allocation (power of two >= 32)
+  uint32_t lo_col;     // column offset of the cross-term accumulator (split only; NT when stacked)
   // ---- EPI_STORE:  C0/C1[m][n] (+)= alpha * acc;  rows m >= msplit go to C1 (row m - msplit)
   float* C0; float* C1; int ldc, msplit, n_store, atomic; float alpha;
-  // ---- EPI_GFT:    row m = k'*Nn + node, column c = b*W + t  ->  G[(b*Nn + node)*3W + k'*W + t] and its 16-bit images
+  // ---- EPI_GFT:    row m' = node*3 + k' (INTERLEAVED Chebyshev terms), column c = b*W + t
+  //                  -> G[(b*Nn + node)*3W + k'*W + t] = G[b][m'][t] (dense (B, 3Nn, W)) and its 16-bit images
   float* G; unsigned short* g_hi; unsigned short* g_lo; int ldh, bf16, Nn, W, BW;
   // ---- EPI_HEAD:   row = (b, node); columns [0,T) forecast pre-activation, [T,T+W) backcast pre-activation
   const float* bf; const float* wfr; const float* bfr; const float* bb; const float* wsc; const float* bsc;
@@ -140,16 +149,30 @@ __device__ __forceinline__ void to_h16(float x, int bf16, unsigned short& hi, un
     lo = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
   }
 }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ void split_granule(const uint4 v, uint4& h, uint4& l) {
+  h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+  l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+  l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+  l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+  l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(S_THREADS, 1)
 tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Tc3Args g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle, by pointer arithmetic on the __shared__ array (an integer round trip would
+  // demote every access below to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
   const int NT = g.NT, S = g.nstage;
   const uint32_t b_bytes = (uint32_t)NT * 128;
-  const uint32_t op_bytes = S_A_BYTES + b_bytes;                 // [A | B] of one precision part
-  const uint32_t stage_bytes = g.split ? 2 * op_bytes : op_bytes;   // split: [A_hi | B_hi | A_lo | B_lo]
+  const bool split = g.split != 0;
+  // stage: split [A_hi | A_lo | B_hi | B_lo], otherwise [A | B]
+  const uint32_t a_lo_off = S_A_BYTES;
+  const uint32_t b_hi_off = split ? 2 * S_A_BYTES : S_A_BYTES;
+  const uint32_t b_lo_off = b_hi_off + b_bytes;
+  const uint32_t stage_bytes = split ? 2 * (S_A_BYTES + b_bytes) : S_A_BYTES + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* conv_bar = empty_bar + S;
@@ -170,7 +193,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     for (int s = 0; s < S; ++s) {
       mb_init(&full_bar[s], 1);
       mb_init(&empty_bar[s], 1);
-      mb_init(&conv_bar[s], 128);
+      mb_init(&conv_bar[s], S_WORKERS);
     }
     mb_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -195,9 +218,9 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         const uint32_t ph = (uint32_t)(i / S) & 1u;
         mb_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* st = smem + (size_t)s * stage_bytes;
-        mb_expect_tx(&full_bar[s], op_bytes);
+        mb_expect_tx(&full_bar[s], S_A_BYTES + b_bytes);
         tma_2d(st, &map_a, &full_bar[s], (kb0 + i) * S_BK, m0);
-        tma_2d(st + S_A_BYTES, &map_b, &full_bar[s], (kb0 + i) * S_BK, n0);
+        tma_2d(st + b_hi_off, &map_b, &full_bar[s], (kb0 + i) * S_BK, n0);
       }
     }
     __syncwarp();
@@ -205,22 +228,30 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // ===== MMA issuer: converged warp, one elected lane =====
     if (num_kb > 0) {
       const uint32_t idesc = idesc_tf32(NT);
+      const uint32_t idesc2 = idesc_tf32(2 * NT);          // stacked [B_hi; B_lo]
+      const uint32_t lo_col = g.lo_col;
+      const bool stacked = g.stacked != 0;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % S;
         const uint32_t ph = (uint32_t)(i / S) & 1u;
-        mb_wait(g.split ? &conv_bar[s] : &full_bar[s], ph);
+        mb_wait(split ? &conv_bar[s] : &full_bar[s], ph);
         tcf_after();
         if (elect1()) {
-          const uint32_t a_hi = s32(smem + (size_t)s * stage_bytes), b_hi = a_hi + S_A_BYTES;
-          const uint32_t a_lo = a_hi + op_bytes, b_lo = b_hi + op_bytes;
+          const uint32_t a_hi = s32(smem + (size_t)s * stage_bytes);
+          const uint32_t a_lo = a_hi + a_lo_off, b_hi = a_hi + b_hi_off, b_lo = a_hi + b_lo_off;
 #pragma unroll
           for (int kk = 0; kk < S_BK / 8; ++kk) {      // 8 tf32 = 32 bytes along K per instruction
             const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
             const uint64_t da = desc_sw128(a_hi + kk * 32), db = desc_sw128(b_hi + kk * 32);
-            umma_tf32(tmem_base, da, db, idesc, acc);
-            if (g.split) {   // cross terms into their own accumulator (file header)
-              umma_tf32(tmem_base + g.lo_col, desc_sw128(a_lo + kk * 32), db, idesc, acc);
-              umma_tf32(tmem_base + g.lo_col, da, desc_sw128(b_lo + kk * 32), idesc, 1u);
+            if (!split) {
+              umma_tf32(tmem_base, da, db, idesc, acc);
+            } else if (stacked) {   // hi.hi -> [0,NT), hi.lo -> [NT,2NT) in one instruction; then lo.hi onto [NT,2NT)
+              umma_tf32(tmem_base, da, db, idesc2, acc);
+              umma_tf32(tmem_base + lo_col, desc_sw128(a_lo + kk * 32), db, idesc, 1u);
+            } else {                // cross terms in their own accumulator (file header)
+              umma_tf32(tmem_base, da, db, idesc, acc);
+              umma_tf32(tmem_base + lo_col, desc_sw128(a_lo + kk * 32), db, idesc, acc);
+              umma_tf32(tmem_base + lo_col, da, desc_sw128(b_lo + kk * 32), idesc, 1u);
             }
           }
           umma_commit(&empty_bar[s]);
@@ -231,8 +262,8 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       __syncwarp();
     }
   } else {
-    // ===== warps 2..5: operand split in shared memory, then the epilogue =====
-    const int tid = threadIdx.x - 64;                 // 0..127
+    // ===== warps 2..9: operand split in shared memory, then the epilogue =====
+    const int tid = threadIdx.x - 64;                 // 0..255
     float *s_wfr = nullptr, *s_wsc = nullptr, *s_bf = nullptr, *s_bfr = nullptr, *s_bb = nullptr, *s_bsc = nullptr,
           *s_fs = nullptr, *s_pb = nullptr, *s_x = nullptr;
     if (EPI == EPI_HEAD) {
@@ -243,40 +274,54 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       s_bfr = s_bf + T;               // [W]
       s_bb = s_bfr + W;               // [W]
       s_bsc = s_bb + W;               // [W]
-      s_fs = s_bsc + W;               // [T][128]  forecast_source of this thread's row (column = thread: conflict free)
+      s_fs = s_bsc + W;               // [T][128]  forecast_source of a row (column = row: conflict free)
       s_pb = s_fs + T * 128;          // [W][128]  backcast pre-activation
       s_x = s_pb + W * 128;           // [W][128]  block input row
-      for (int i = tid; i < W * T; i += 128) s_wfr[i] = __ldg(g.wfr + i);
-      for (int i = tid; i < T; i += 128) s_bf[i] = __ldg(g.bf + i);
-      for (int i = tid; i < W; i += 128) s_bfr[i] = __ldg(g.bfr + i);
+      for (int i = tid; i < W * T; i += S_WORKERS) s_wfr[i] = __ldg(g.wfr + i);
+      for (int i = tid; i < T; i += S_WORKERS) s_bf[i] = __ldg(g.bf + i);
+      for (int i = tid; i < W; i += S_WORKERS) s_bfr[i] = __ldg(g.bfr + i);
       if (g.bc_bnw != nullptr) {
-        for (int i = tid; i < W * W; i += 128) s_wsc[i] = __ldg(g.wsc + i);
-        for (int i = tid; i < W; i += 128) {
+        for (int i = tid; i < W * W; i += S_WORKERS) s_wsc[i] = __ldg(g.wsc + i);
+        for (int i = tid; i < W; i += S_WORKERS) {
           s_bb[i] = __ldg(g.bb + i);
           s_bsc[i] = __ldg(g.bsc + i);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (num_kb > 0) {
-      if (g.split) {
-        const uint32_t n16 = op_bytes >> 4;           // 16-byte granules of [A | B]
+      if (split) {
+        const uint32_t na = S_A_BYTES >> 4, nb = b_bytes >> 4;      // 16-byte granules of the A / B tile
+        const uint32_t n16 = na + nb;
         for (int i = 0; i < num_kb; ++i) {
           const int s = i % S;
           const uint32_t ph = (uint32_t)(i / S) & 1u;
           mb_wait(&full_bar[s], ph);
-          uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
-          uint4* lo = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + op_bytes);
-          for (uint32_t q = tid; q < n16; q += 128) {
-            const uint4 v = hi[q];
-            uint4 h, l;
-            h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            hi[q] = h;
-            lo[q] = l;
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          for (uint32_t q0 = tid; q0 < n16; q0 += 4 * S_WORKERS) {   // 4 granules in flight per thread
+            uint4 v[4];
+            uint4* ph_[4];
+            uint4* pl_[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t q = q0 + u * S_WORKERS;
+              const bool ok = q < n16;
+              const uint32_t qq = ok ? q : tid;
+              const bool isa = qq < na;
+              ph_[u] = reinterpret_cast<uint4*>(st + (isa ? 0u : b_hi_off)) + (isa ? qq : qq - na);
+              pl_[u] = reinterpret_cast<uint4*>(st + (isa ? a_lo_off : b_lo_off)) + (isa ? qq : qq - na);
+              if (!ok) ph_[u] = nullptr;
+              v[u] = ok ? *ph_[u] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (ph_[u] != nullptr) {
+                uint4 h, l;
+                split_granule(v[u], h, l);
+                *ph_[u] = h;
+                *pl_[u] = l;
+              }
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
           mb_arrive(&conv_bar[s]);
@@ -285,11 +330,14 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       mb_wait(tmem_full_bar, 0);
       tcf_after();
       const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
+      const int half = (warp - 2) >> 2;               // the two warps of a quarter split the columns
       const int rloc = quarter * 32 + lane;
       const int row = m0 + rloc;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const uint32_t lo_col = g.lo_col;
-      const bool split = g.split != 0;
+      const int nchunk = NT / 16;
+      const int c_split = ((nchunk + 1) / 2) * 16;
+      const int c_begin = half ? c_split : 0, c_end = half ? NT : c_split;
       // 16 accumulator columns of this thread's row: main (+ cross-term accumulator)
       auto load16 = [&](int c, float (&v)[16]) {
         tmem_ld16(taddr + c, v);
@@ -307,7 +355,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       if (EPI == EPI_STORE) {
         float* crow = nullptr;
         if (row < g.M) crow = row < g.msplit ? g.C0 + (size_t)row * g.ldc : g.C1 + (size_t)(row - g.msplit) * g.ldc;
-        for (int c = 0; c < NT; c += 16) {
+        for (int c = c_begin; c < c_end; c += 16) {
           float v[16];
           load16(c, v);
           if (crow != nullptr) {
@@ -322,42 +370,81 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           }
         }
       } else if (EPI == EPI_GFT) {
+        // Stage the tile in shared memory as [b_local][row][t] — with interleaved rows m' = node*3 + k' that IS the layout
+        // of G for one batch element (G[b][m'][t], dense) — then write it out with coalesced 16-byte stores.  All MMAs have
+        // completed (tmem_full_bar), so the operand ring is free to be reused as the staging buffer.
         const int Nn = g.Nn, W = g.W;
-        const bool valid = row < g.M;
-        const int kp = valid ? row / Nn : 0, node = valid ? row - kp * Nn : 0;
-        for (int c = 0; c < NT; c += 16) {
+        float* s_out = reinterpret_cast<float*>(smem);
+        for (int c = c_begin; c < c_end; c += 16) {
           float v[16];
           load16(c, v);
-          if (valid) {
-            const int c0 = n0 + c;
-            int b = c0 / W, t = c0 - b * W;
+          int bl = c / W, t = c - bl * W;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j < g.BW) {
-                const long long ro = (long long)b * Nn + node;
-                if (g.G != nullptr) g.G[ro * (3 * W) + kp * W + t] = v[j];
-                if (g.g_hi != nullptr) {
-                  unsigned short hh, ll;
-                  to_h16(v[j], g.bf16, hh, ll);
-                  g.g_hi[ro * g.ldh + kp * W + t] = hh;
-                  if (!g.bf16) g.g_lo[ro * g.ldh + kp * W + t] = ll;
-                }
+          for (int j = 0; j < 16; ++j) {
+            s_out[(bl * S_BM + rloc) * W + t] = v[j];
+            if (++t == W) { t = 0; ++bl; }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int nv = min(S_BM, g.M - m0);                 // valid rows of this tile
+        const int nbl = NT / W;                             // batch elements per tile (NT is a multiple of W)
+        const int b0 = n0 / W;
+        const bool vec = (W & 3) == 0 && (((size_t)3 * Nn * W) & 3) == 0;
+        for (int bl = 0; bl < nbl; ++bl) {
+          const int b = b0 + bl;
+          if (b * W >= g.BW) break;
+          const float* src = s_out + (size_t)bl * S_BM * W;
+          if (g.G != nullptr) {
+            float* dst = g.G + ((size_t)b * 3 * Nn + m0) * W;
+            const int nel = nv * W;
+            if (vec) {
+              for (int e = tid * 4; e < nel; e += 4 * S_WORKERS)
+                *reinterpret_cast<float4*>(dst + e) = *reinterpret_cast<const float4*>(src + e);
+            } else {
+              for (int e = tid; e < nel; e += S_WORKERS) dst[e] = src[e];
+            }
+          }
+          if (g.g_hi != nullptr) {
+            if ((W & 3) == 0 && (g.ldh & 3) == 0) {          // 4 halves = 8 bytes per store
+              const int upr = W / 4;                         // units per (row, k') chunk
+              for (int it = tid; it < nv * upr; it += S_WORKERS) {
+                const int rl = it / upr, u = it - rl * upr;
+                const int mp = m0 + rl, node = mp / 3, kp = mp - node * 3;
+                const float4 f = *reinterpret_cast<const float4*>(src + rl * W + 4 * u);
+                unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
+                to_h16(f.x, g.bf16, h0, l0); to_h16(f.y, g.bf16, h1, l1);
+                to_h16(f.z, g.bf16, h2, l2); to_h16(f.w, g.bf16, h3, l3);
+                const size_t o = ((size_t)b * Nn + node) * g.ldh + kp * W + 4 * u;
+                *reinterpret_cast<uint2*>(g.g_hi + o) =
+                    make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+                if (!g.bf16)
+                  *reinterpret_cast<uint2*>(g.g_lo + o) =
+                      make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
               }
-              if (++t == W) { t = 0; ++b; }
+            } else {
+              for (int it = tid; it < nv * W; it += S_WORKERS) {
+                const int rl = it / W, t = it - rl * W;
+                const int mp = m0 + rl, node = mp / 3, kp = mp - node * 3;
+                unsigned short hh, ll;
+                to_h16(src[it], g.bf16, hh, ll);
+                const size_t o = ((size_t)b * Nn + node) * g.ldh + kp * W + t;
+                g.g_hi[o] = hh;
+                if (!g.bf16) g.g_lo[o] = ll;
+              }
             }
           }
         }
       } else {   // EPI_HEAD
         const int T = g.T, W = g.W;
         const bool valid = row < g.M;
-        for (int c = 0; c < NT; c += 16) {
+        for (int c = c_begin; c < c_end; c += 16) {
           float v[16];
           load16(c, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int u = c + j;
             if (u < T) {
-              const float f = sigmoidf_(v[j] + s_bf[u]);
+              const float f = fast_sigmoid(v[j] + s_bf[u]);
               s_fs[u * 128 + rloc] = f;
               if (valid && g.save_fs != nullptr) g.save_fs[(long long)row * T + u] = f;
             } else if (u < T + W) {
@@ -365,21 +452,25 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             }
           }
         }
+        const bool has_bc = g.bc_bnw != nullptr;
+        if (valid && has_bc && half == 0)
+          for (int t = 0; t < W; ++t) s_x[t * 128 + rloc] = g.x_bnw[(long long)row * W + t];
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // a row's columns were produced by two warps
         if (valid) {
-          const bool has_bc = g.bc_bnw != nullptr;
-          if (has_bc)
-            for (int t = 0; t < W; ++t) s_x[t * 128 + rloc] = g.x_bnw[(long long)row * W + t];
           const int b = row / g.Nn, node = row - b * g.Nn;
-          for (int o = 0; o < W; ++o) {
+          const int o_split = (W + 1) / 2;
+          const int o0 = half ? o_split : 0, o1 = half ? W : o_split;   // the two warps of a row split the outputs
+          for (int o = o0; o < o1; ++o) {
             float acc = s_bfr[o];
             const float* wr = s_wfr + o * T;
+#pragma unroll 4
             for (int u = 0; u < T; ++u) acc = fmaf(s_fs[u * 128 + rloc], wr[u], acc);
             g.forecast[(long long)row * W + o] = acc;
             if (has_bc) {
               float sc = s_bsc[o];
               const float* ws = s_wsc + o * W;
               for (int t = 0; t < W; ++t) sc = fmaf(s_x[t * 128 + rloc], ws[t], sc);
-              const float bc = sigmoidf_(s_pb[o * 128 + rloc] + s_bb[o] - sc);
+              const float bc = fast_sigmoid(s_pb[o * 128 + rloc] + s_bb[o] - sc);
               g.bc_bnw[(long long)row * W + o] = bc;
               g.bc_bwn[((long long)b * W + o) * g.Nn + node] = bc;
               if (g.bc_pad != nullptr) g.bc_pad[((long long)b * W + o) * g.ld_pad + node] = bc;
@@ -427,19 +518,27 @@ bool map_f32(EncodeFn enc, CUtensorMap* map, const float* base, int rows, int co
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-uint32_t tmem_cols_for(int nt) {
+uint32_t pow2_cols(int n) {
   uint32_t c = 32;
-  while ((int)c < nt) c <<= 1;
+  while ((int)c < n) c <<= 1;
   return c;
+}
+// accumulator placement for a tile of NT columns
+void plan_tmem(Tc3Args* g) {
+  const int NT = g->NT;
+  g->stacked = (g->split && 2 * NT <= 256) ? 1 : 0;
+  if (!g->split) { g->lo_col = 0; g->tmem_cols = pow2_cols(NT); }
+  else if (g->stacked) { g->lo_col = (uint32_t)NT; g->tmem_cols = pow2_cols(2 * NT); }
+  else { g->lo_col = pow2_cols(NT); g->tmem_cols = 2 * pow2_cols(NT); }
 }
 
 // ring depth and dynamic shared memory for a tile shape; returns 0 stages when it does not fit
-int plan_smem(int NT, int split, size_t extra, int max_stages, size_t* smem_out) {
+int plan_smem(int NT, int split, size_t extra, size_t min_ring, int max_stages, size_t* smem_out) {
   const size_t stage = (size_t)(split ? 2 : 1) * (S_A_BYTES + (size_t)NT * 128);
   const size_t fixed = 1024 /* alignment slack */ + 256 /* barriers + tmem slot */ + extra;
   int s = max_stages;
   while (s >= 2 && fixed + (size_t)s * stage > 227 * 1024) --s;
-  if (s < 2) return 0;
+  if (s < 2 || (size_t)s * stage < min_ring) return 0;
   *smem_out = fixed + (size_t)s * stage;
   return s;
 }
@@ -462,23 +561,34 @@ int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const Tc3Args& g, d
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+int lcm_i(int a, int b) {
+  int x = a, y = b;
+  while (y) { const int t = x % y; x = y; y = t; }
+  return a / x * b;
+}
+
 }  // namespace
 
-// dst[r][c] = src[r][c] for c < cols (row pitches ld_src / ld_dst): TMA-able (pitch % 4 == 0) copy of an operand
+// dst[r'][c] = src[r][c] for c < cols (row pitches ld_src / ld_dst): TMA-able (pitch % 4 == 0) copy of an operand, with
+// an optional row permutation:  stack_n == 0:  r' = r*row_mul + row_add;   stack_n > 0 (the source is a stack of matrices of
+// stack_n rows each, r = k*stack_n + i):  r' = i*row_mul + k + row_add.  (row_mul = 3: the interleaved row order
+// node*3 + k' of the graph-Fourier kernel's A operand.)
 __global__ void pad_rows_kernel(const float* __restrict__ src, long long rows, int cols, int ld_src,
-                                float* __restrict__ dst, int ld_dst) {
+                                float* __restrict__ dst, int ld_dst, int row_mul, int row_add, int stack_n) {
   const long long total = rows * cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long r = idx / cols;
     const int c = (int)(idx - r * cols);
-    dst[r * ld_dst + c] = src[r * ld_src + c];
+    const long long rd = stack_n > 0 ? (r % stack_n) * row_mul + r / stack_n + row_add : r * row_mul + row_add;
+    dst[rd * ld_dst + c] = src[r * ld_src + c];
   }
 }
-int launch_pad_rows(const float* src, long long rows, int cols, int ld_src, float* dst, int ld_dst, cudaStream_t st) {
+int launch_pad_rows(const float* src, long long rows, int cols, int ld_src, float* dst, int ld_dst, cudaStream_t st,
+                    int row_mul, int row_add, int stack_n) {
   const long long total = rows * cols;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  pad_rows_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst);
+  pad_rows_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst, row_mul, row_add, stack_n);
   SG_LAUNCH_CHECK("pad_rows_kernel");
   return 0;
 }
@@ -493,10 +603,11 @@ int tc3_gemm(int M, int N, int K, float alpha, const float* A, int lda, const fl
   CUtensorMap ma, mb;
   if (!map_f32(enc, &ma, A, M, K, lda, S_BM) || !map_f32(enc, &mb, B, n_rows_b, K, ldb, N)) return -1;
   size_t smem = 0;
-  const int ns = plan_smem(N, split_ops, 0, 4, &smem);
+  const int ns = plan_smem(N, split_ops, 0, 0, 4, &smem);
   if (ns == 0) return -1;
   Tc3Args g = {};
-  g.M = M; g.K = K; g.NT = N; g.nstage = ns; g.split = split_ops; g.lo_col = tmem_cols_for(N); g.tmem_cols = tmem_cols_for(N) * (split_ops ? 2 : 1);
+  g.M = M; g.K = K; g.NT = N; g.nstage = ns; g.split = split_ops;
+  plan_tmem(&g);
   g.C0 = C0; g.C1 = C1 != nullptr ? C1 : C0; g.ldc = ldc; g.msplit = C1 != nullptr ? msplit : M;
   g.n_store = n_store; g.atomic = atomic; g.alpha = alpha;
   if (splits < 1) splits = 1;
@@ -504,7 +615,8 @@ int tc3_gemm(int M, int N, int K, float alpha, const float* A, int lda, const fl
 }
 
 // gfted rows for the GLU chain: G[(b*N + n)*3W + k'*W + t] = sum_m mul_L[k'+1][n][m] x[b][t][m]  (+ 16-bit images).
-// mul_Lp: (3N, ldl) = mul_L[1..3] with a TMA-able pitch; xp: (B*W, ldx).  Returns -1 when unsupported.
+// mul_Lp: (3N, ldl) with INTERLEAVED rows, row n*3 + k' = mul_L[k'+1][n][:] (TMA-able pitch); xp: (B*W, ldx).
+// Returns -1 when unsupported.
 int gft_tc(const float* mul_Lp, int ldl, const float* xp, int ldx, float* G, unsigned short* g_img, int ldh, int bf16,
            int B, int N, int W, int split_ops, cudaStream_t st) {
   static const bool off = getenv("STEMGNN_NO_GFT_TC") != nullptr;
@@ -513,14 +625,18 @@ int gft_tc(const float* mul_Lp, int ldl, const float* xp, int ldx, float* G, uns
   if (g_img != nullptr && ((ldh & 1) != 0 || ldh < 3 * W)) return -1;
   EncodeFn enc = encode_fn();
   if (enc == nullptr) return -1;
-  const int NT = 32, M = 3 * N, BW = B * W;
+  // column tile = whole batch elements (the epilogue writes G[b][tile rows][0..W) as one dense block per b)
+  const int NT = lcm_i(W, 16);
+  if (NT > 128) return -1;
+  const int M = 3 * N, BW = B * W;
   CUtensorMap ma, mb;
   if (!map_f32(enc, &ma, mul_Lp, M, N, ldl, S_BM) || !map_f32(enc, &mb, xp, BW, N, ldx, NT)) return -1;
   size_t smem = 0;
-  const int ns = plan_smem(NT, split_ops, 0, 4, &smem);
+  const int ns = plan_smem(NT, split_ops, 0, (size_t)S_BM * NT * sizeof(float), 4, &smem);   // ring doubles as the staging tile
   if (ns == 0) return -1;
   Tc3Args g = {};
-  g.M = M; g.K = N; g.NT = NT; g.nstage = ns; g.split = split_ops; g.lo_col = tmem_cols_for(NT); g.tmem_cols = tmem_cols_for(NT) * (split_ops ? 2 : 1);
+  g.M = M; g.K = N; g.NT = NT; g.nstage = ns; g.split = split_ops;
+  plan_tmem(&g);
   g.G = G; g.g_hi = g_img; g.g_lo = g_img != nullptr ? g_img + (size_t)B * N * ldh : nullptr; g.ldh = ldh; g.bf16 = bf16;
   g.Nn = N; g.W = W; g.BW = BW;
   return launch_tc3<EPI_GFT>(ma, mb, g, dim3(ceil_div(M, S_BM), ceil_div(BW, NT), 1), smem, st, "tc3_kernel<gft>");
@@ -541,10 +657,11 @@ int out_head_tc(const float* act3, int K, const float* woutT, int PWp, const Hea
   if (!map_f32(enc, &ma, act3, R, K, K, S_BM) || !map_f32(enc, &mb, woutT, PWp, K, K, PWp)) return -1;
   const size_t extra = sizeof(float) * ((size_t)W * T + (size_t)W * W + T + 3 * (size_t)W + (size_t)(T + 2 * W) * 128) + 64;
   size_t smem = 0;
-  const int ns = plan_smem(PWp, split_ops, extra, 4, &smem);
+  const int ns = plan_smem(PWp, split_ops, extra, 0, 4, &smem);
   if (ns == 0) return -1;
   Tc3Args g = {};
-  g.M = R; g.K = K; g.NT = PWp; g.nstage = ns; g.split = split_ops; g.lo_col = tmem_cols_for(PWp); g.tmem_cols = tmem_cols_for(PWp) * (split_ops ? 2 : 1);
+  g.M = R; g.K = K; g.NT = PWp; g.nstage = ns; g.split = split_ops;
+  plan_tmem(&g);
   g.Nn = h.N; g.W = W; g.T = T;
   g.bf = h.bf; g.wfr = h.wfr; g.bfr = h.bfr; g.bb = h.bb; g.wsc = h.wsc; g.bsc = h.bsc;
   g.x_bnw = h.x_bnw; g.forecast = h.forecast; g.bc_bnw = h.backcast_bnw; g.bc_bwn = h.backcast_bwn;
