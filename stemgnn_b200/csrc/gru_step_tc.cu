@@ -140,13 +140,16 @@ struct StepArgs {
 __global__ void __launch_bounds__(ST_THREADS, 1)
 gru_step_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, StepArgs t) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by pointer arithmetic on the __shared__ array (an integer round trip demotes every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (sa(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
   float* gh_sm = reinterpret_cast<float*>(stages + ST_NSTG * ST_STAGE);     // [120][32]
   float* wih_sm = gh_sm + 3 * ST_U * ST_SEQ;                                 // [120][W]
   float* bias_sm = wih_sm + 3 * ST_U * t.a.W;                                // [4][40]
   float* x_sm = bias_sm + 4 * ST_U;                                          // [32][W]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(x_sm + ST_SEQ * t.a.W + 1) & ~uintptr_t(7));
+  uint8_t* bar_base = reinterpret_cast<uint8_t*>(x_sm + ST_SEQ * t.a.W);
+  bar_base += (8u - (sa(bar_base) & 7u)) & 7u;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + ST_NSTG;
   uint64_t* tfull = empty_bar + ST_NSTG;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);

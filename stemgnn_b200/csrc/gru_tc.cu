@@ -237,7 +237,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, uint4 a, uint4 b) {
 template <int PP>
 __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs ta) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by pointer arithmetic on the __shared__ array: an integer round trip demotes EVERY shared-memory access of the
+  // step loop to generic LD/ST (612 LD.E + 360 LD.E.128 in the SASS of the previous build)
+  uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
   const GruArgs& a = ta.a;
   const GruTcGeom g = ta.g;
   const int U = g.U, CS = g.CS, G = ta.G;
@@ -249,12 +251,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_tc_cluster_kernel(GruTcArgs
   float* wih_sm = gh_sm + 128 * GT_GMAX;                  // [3U][W]
   float* bias_sm = wih_sm + 3 * U * W;                    // [3U] b_ih (+ b_hh for r,z) and [U] b_hn
   __half* stage_sm = reinterpret_cast<__half*>(bias_sm + 4 * U);      // [2][8][U] (16-byte aligned: U % 8 == 0)
-  uint64_t* hbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(stage_sm + 2 * GT_GMAX * U + 7) & ~uintptr_t(7));
+  uint8_t* hbar_base = reinterpret_cast<uint8_t*>(stage_sm + 2 * GT_GMAX * U);
+  hbar_base += (8u - (s_u32(hbar_base) & 7u)) & 7u;
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(hbar_base);
   uint64_t* tfull = hbar + 2 * 16;                        // hbar[buf][source]
   uint64_t* xbar = tfull + GT_ROUNDS;                     // tfull[r]: accumulator set r complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 1);
   uint32_t* rdy_sm = tmem_slot + 2;                       // [16] rdy[r]: K steps of round r, rdy[8 + r]: last arrival index of round r
-  float* xs_sm = reinterpret_cast<float*>(reinterpret_cast<uintptr_t>(rdy_sm + 16 + 3) & ~uintptr_t(15));     // [N][G][W]
+  uint8_t* xs_base = reinterpret_cast<uint8_t*>(rdy_sm + 16);
+  xs_base += (16u - (s_u32(xs_base) & 15u)) & 15u;
+  float* xs_sm = reinterpret_cast<float*>(xs_base);       // [N][G][W]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int q = (int)cluster.block_rank();
