@@ -560,7 +560,7 @@ static int block_backward(const stemgnn_dims_t& dm, const stemgnn_block_params_t
           // weight gradients: [dWl; dWr] (2d x d) += dlrT (2d x R) . inT (d x R)^T   (K = R, split-K atomics)
           SG_TRY(transpose(st, in, R, d, d, w.inT, ldT));
           rc = tc_gemm(2 * d, d, R, 1.f, w.dlrT, ldT, w.inT, ldT, d, gr.glu_left_w[gidx], gr.glu_right_w[gidx], d, d,
-                       d, 1, 12, st, gemm_mode == 0 ? -1 : 0);
+                       d, 1, 36, st, gemm_mode == 0 ? -1 : 0);   // 4 row tiles x 36 K splits = 144 CTAs (one wave)
           if (rc > 0) return rc;
           if (rc == 0) {
             // input gradient: d_in (R x d) = dlr (R x 2d) . [Wl^T | Wr^T] (d x 2d)^T
@@ -732,7 +732,7 @@ int model_backward(const stemgnn_dims_t* dims, const stemgnn_params_t* p, const 
         const int nn_ = N - n0 < 256 ? N - n0 : 256;
         const int npad = (nn_ + 15) / 16 * 16;
         rc = tc_gemm(3 * N, npad, Kr, 1.f, w.dghT, ldT, w.hT + (size_t)n0 * ldT, ldT, nn_, gr.gru_w_hh + n0, nullptr,
-                     0, N, nn_, 1, 8, st, opts->gemm_mode == 0 ? -1 : 0);
+                     0, N, nn_, 1, 16, st, opts->gemm_mode == 0 ? -1 : 0);
         if (rc > 0) return rc;
         // a chunk that is unsupported AFTER earlier chunks were accumulated must not fall back to the full fp32 product
         // (it would double-count the finished columns)

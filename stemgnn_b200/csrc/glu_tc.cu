@@ -154,7 +154,7 @@ glu_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               const __grid_constant__ CUtensorMap map_wr, GluTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle pattern
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
   const int N = g.N;
   constexpr int RB = BK * 4;                        // bytes per tile row
   constexpr int NSTAGE = BK == 32 ? 2 : 5;
@@ -308,7 +308,7 @@ glu_chain_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
                     const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w3l,
                     const __grid_constant__ CUtensorMap map_w3r, GluChainArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
   constexpr int NSTG = 3;
   constexpr uint32_t A_CHUNK = TC_BM * 128;            // 128 rows x 32 fp32
   const int N = g.N;
@@ -485,7 +485,7 @@ struct TcGemmArgs {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS)
   const int N = g.N;
   const uint32_t a_bytes = TC_BM * 128, w_bytes = (uint32_t)N * 128;
   const uint32_t stage_bytes = a_bytes + w_bytes;

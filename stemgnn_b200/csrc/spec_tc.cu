@@ -7,8 +7,8 @@
 //
 // One kernel, three epilogues.  kind::tf32 reads 10 mantissa bits of an fp32 operand; a single pass therefore carries
 // ~2^-10 relative operand error (round 1's "truncated TF32", which met the 1e-3 / 1e-4 tolerance only at the model
-// output).  Here every operand is x = hi + lo with hi = x & 0xffffe000 (exactly representable in TF32, so the result does
-// not depend on whether the tensor core truncates or rounds) and lo = x - hi (exact in fp32, <= 13 significant bits), and
+// output).  Here every operand is x = hi + lo with hi = x & 0xffffe000 (what the tensor core reads of the raw fp32 word:
+// it truncates, see split_granule) and lo = x - hi (exact in fp32, <= 13 significant bits), and
 // each 8-wide K step issues hi.hi into one fp32 accumulator in tensor memory and hi.lo + lo.hi into a SECOND one; the epilogue
 // adds the two.  Operand error ~2^-21.  (Why two accumulators: the tensor core truncates the running sum at every accumulating
 // MMA — measured, the error of a split product grows linearly with K, 4e-6 of max|C| at K = 480 with all three products in one
@@ -17,8 +17,9 @@
 //
 // Pipeline per 32-column K block (one 128-byte swizzle row), 320 threads:
 //   warp 0        TMA producer: fp32 tiles of A (128 rows) and B (NT rows), 128B-swizzled, K tail / row tail zero-filled
-//   warps 2..9    converters: mask the tile in place to `hi`, write `lo` to a second tile of the same (swizzled) layout —
-//                 the transform is elementwise, so it is layout agnostic — fence.proxy.async, arrive on conv_bar
+//   warps 2..9    converters: write `lo` to a second tile of the same (swizzled) layout — the transform is elementwise, so
+//                 it is layout agnostic; the TMA-written tile itself serves as `hi` (the tensor core truncates it) —
+//                 fence.proxy.async, arrive on conv_bar
 //   warp 1        converged warp, elected lane issues the tcgen05.mma of a K step; tcgen05.commit frees the stage.
 //                 Stage layout [A_hi | A_lo | B_hi | B_lo]: when 2*NT <= 256 the B operand of the first MMA is the STACKED
 //                 tile [B_hi; B_lo] (N = 2*NT), so A_hi is read once for hi.hi (columns [0,NT)) and hi.lo (columns [NT,2NT));
@@ -150,6 +151,14 @@ __device__ __forceinline__ void to_h16(float x, int bf16, unsigned short& hi, un
   }
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// lo = x - (x & 0xffffe000).  The `hi` tile is NOT rewritten: kind::tf32 truncates its operands to the top 19 bits (measured:
+// the error of a single pass on seeded inputs equals the truncation model to 3 digits on every tested shape — 6.42e-4 /
+// 9.35e-4 / 7.19e-4 / 7.92e-4 — where round-to-nearest would give 4.18e-4 / 3.83e-4 / 2.76e-4 / 3.78e-4; profiles/README.md),
+// so the raw fp32 tile already IS the hi operand.  If a future part rounded instead, tests/test_spec_tc_gpu.py would fail at
+// the 1e-4 level; S_MASK_HI = 1 restores the explicit mask (one more 16-byte shared store per granule).
+#ifndef S_MASK_HI
+#define S_MASK_HI 0
+#endif
 __device__ __forceinline__ void split_granule(const uint4 v, uint4& h, uint4& l) {
   h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
   l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
@@ -318,7 +327,7 @@ tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
               if (ph_[u] != nullptr) {
                 uint4 h, l;
                 split_granule(v[u], h, l);
-                *ph_[u] = h;
+                if (S_MASK_HI) *ph_[u] = h;
                 *pl_[u] = l;
               }
             }
