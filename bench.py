@@ -293,22 +293,34 @@ def run_ours(args, rank, world, local_rank):
             sys.stderr.write(f"[bench] GLU chain timing failed: {exc}\n")
 
         # ---- end to end through the public API with host buffers ----------------------------------
+        # public API for host buffers: Model.inference_session(B) — per call: H2D of the batch into the captured graph's static
+        # input, ONE graph replay of the forward, D2H of the forecast (stemgnn_b200/session.py).  Also timed: the plain
+        # `model(x_host.to(dev))` loop (the reference's inference loop shape, handler.py:34-40), reported beside it.
         out_host = torch.empty(B, H, N).pin_memory()
         for _ in range(3):
             f, _a = model(x_host.to(dev, non_blocking=True))
             out_host.copy_(f, non_blocking=True)
         barrier()
-        sys.stderr.write(f"[bench] before e2e: graph captures {(model._rt or {}).get('captures')}\n")
         t0 = time.perf_counter()
         for _ in range(steps):
             xd = x_host.to(dev, non_blocking=True)                      # H2D of the step's input
             f, _a = model(xd)
             out_host.copy_(f, non_blocking=True)                        # D2H of the step's result
             torch.cuda.synchronize()
+        e2e_plain_s = time.perf_counter() - t0
+        sess = model.inference_session(B)
+        for _ in range(3):
+            sess(x_host, out_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sess(x_host, out_host)                                      # H2D + graph replay + D2H, stream-ordered
+            torch.cuda.synchronize()                                    # the step's result is on the host
         e2e_s = time.perf_counter() - t0
         barrier()
-        sys.stderr.write(f"[bench] e2e {e2e_s / steps * 1e3:.3f} ms/step; graph captures so far: "
-                         f"{(model._rt or {}).get('captures')}, use_cuda_graph={model.use_cuda_graph}\n")
+        e2e_forecast = out_host.clone()
+        sys.stderr.write(f"[bench] e2e session {e2e_s / steps * 1e3:.3f} ms/step, plain Model.forward loop "
+                         f"{e2e_plain_s / steps * 1e3:.3f} ms/step\n")
 
     # ---- second column: training step (handler.py:160-165) ----------------------------------------------
     train = None
@@ -389,7 +401,14 @@ def run_ours(args, rank, world, local_rank):
             "parity": parity,
             "e2e": {"value": world * B * steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": B * W * N * 4, "d2h_bytes_per_step": B * H * N * 4,
-                    "ms_per_step": e2e_ms / steps},
+                    "ms_per_step": e2e_ms / steps,
+                    "api": "Model.inference_session(B)(x_pinned, out_pinned) + torch.cuda.synchronize() per step: H2D of the batch, "
+                           "one CUDA-graph replay, D2H of the forecast",
+                    "max_abs_diff_vs_device_timed_forecast": float((e2e_forecast - forecast_ours).abs().max()),
+                    "plain_forward_loop": {"value": B * steps / e2e_plain_s, "unit": "windows/s (rank 0)",
+                                           "ms_per_step": e2e_plain_s / steps * 1e3,
+                                           "what": "x_host.to(dev) -> model(x) -> out_host.copy_(forecast) -> synchronize "
+                                                   "(Model.forward re-validates ~70 parameter pointers / versions per call)"}},
             "train": None if not train else {
                 "value": world * B * train["steps"] / (train_ms * 1e-3), "unit": "windows/s",
                 "ms_per_step": train_ms / train["steps"], "steps": train["steps"], "what": train["what"]},

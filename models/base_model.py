@@ -270,6 +270,12 @@ class Model(nn.Module):
         rt["folded_for"] = (key, versions, self.gemm_mode)       # only after a successful call
         return out
 
+    def inference_session(self, batch_size):
+        """Frozen-weight inference from / to host buffers: one H2D, one CUDA-graph replay, one D2H per call
+        (`stemgnn_b200/session.py`; the reference's `inference` loop, handler.py:34-40, without per-call host work)."""
+        from stemgnn_b200.session import InferenceSession
+        return InferenceSession(self, batch_size)
+
     def forward(self, x, dropout_mask=None):
         """x: (B, W, N) float32 CUDA tensor.  `dropout_mask` (optional, tests): explicit {0,1}
         keep-mask (B,N,N) replacing the Philox mask in training mode."""

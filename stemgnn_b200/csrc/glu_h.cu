@@ -327,18 +327,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
       const float* sbr = s_bias + (l * 2 + 1) * N;
       float* gout = l == 2 ? g.out3 : g.act[l];
       const int ldo = l == 2 ? g.ldo3 : N;
-      // software-pipelined tensor-memory loads: the next 16 columns are in flight while these are gated and written
-      float lv[16], rv[16], ln[16], rn[16];
-      ld16(taddr + c_begin, lv);
-      ld16(taddr + H_RIGHT_COL + c_begin, rv);
-      ld_wait();
       for (int c = c_begin; c < c_end; c += 16) {
-        float o[16];
-        const bool more = c + 16 < c_end;
-        if (more) {
-          ld16(taddr + c + 16, ln);
-          ld16(taddr + H_RIGHT_COL + c + 16, rn);
-        }
+        float lv[16], rv[16], o[16];
+        ld16(taddr + c, lv);
+        ld16(taddr + H_RIGHT_COL + c, rv);
+        ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           lv[j] += sbl[c + j];
@@ -380,14 +373,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) glu_chain_h_kernel(const __grid_
               pl[j] = make_float4(lv[4 * j], lv[4 * j + 1], lv[4 * j + 2], lv[4 * j + 3]);
               ps[j] = make_float4(rv[4 * j], rv[4 * j + 1], rv[4 * j + 2], rv[4 * j + 3]);
             }
-          }
-        }
-        if (more) {
-          ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            lv[j] = ln[j];
-            rv[j] = rn[j];
           }
         }
       }

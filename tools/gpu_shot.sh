@@ -1,10 +1,15 @@
 #!/bin/bash
+# full GPU suite + smoke + the bench line
 mkdir -p gpurun_out
-run() { name=$1; shift; ( time timeout 600 "$@" ) > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log; }
-run t_par python -m pytest tests/test_spec_tc_gpu.py tests/test_glu_tc_gpu.py tests/test_forward_parity_gpu.py tests/test_backward_parity_gpu.py tests/test_trainer_gpu.py -q -x
-grep -E "passed|failed|FAILED|Error" gpurun_out/t_par.log | tail -10
-run ab_default python tools/ab_time.py prof
-STEMGNN_TC_NOSPLIT=1 run ab_nosplit python tools/ab_time.py
-grep -h "^\[" gpurun_out/ab_*.log
-grep -A12 "eager eval forward" gpurun_out/ab_default.log | cut -c1-60,140-250 | tail -10
-grep -A8 "eager train step" gpurun_out/ab_default.log | cut -c1-60,140-250 | tail -6
+( time timeout 800 python -m pytest tests/ -q -m gpu -x ) > gpurun_out/t_full.log 2>&1; echo "rc=$?" >> gpurun_out/t_full.log
+grep -E "passed|failed|FAILED|Error|rc=" gpurun_out/t_full.log | tail -8
+( timeout 200 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+( timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_cfg2.json ) 2> gpurun_out/bench_cfg2.err; tail -c 400 gpurun_out/bench_cfg2.err
+python - <<'PY'
+import json
+try:
+    d = json.loads(open('gpurun_out/bench_cfg2.json').read().strip().splitlines()[-1])
+    print({k: d[k] for k in ('value', 'ms_per_step', 'gpu_launches')}); print(d['e2e']); print(d['parity']); print(d['train']); print(d['roofline']['ms_per_launch'], d['roofline']['frac'], d['clocks'])
+except Exception as e:
+    print('bench parse failed', e)
+PY
