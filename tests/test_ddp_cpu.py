@@ -87,3 +87,46 @@ def test_shard_indices_padding_and_determinism():
     assert ddp.world_size() == 1
     t = torch.ones(3)
     assert ddp.allreduce_mean_(t) is t                           # single process: no-op
+
+
+def _graph_allreduce_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from stemgnn_b200 import ddp, runtime
+    ddp.init_from_env(backend="gloo")
+    # a stand-in "workspace": the library hands the hook raw pointers INTO it; the hook must average exactly that range
+    ws = torch.zeros(4096, dtype=torch.uint8)
+    view = ws[256:256 + 4 * 10].view(torch.float32)
+    view.copy_(torch.arange(10, dtype=torch.float32) * (rank + 1))
+    sentinel = ws[:256].clone(), ws[256 + 40:].clone()
+    ga = runtime.GraphAllreduce(ws, None)
+    ga.fn(ws.data_ptr() + 256, 10, None, None)           # what stemgnn_model_forward does through the function pointer
+    ga.check()
+    ok_bounds = torch.equal(ws[:256], sentinel[0]) and torch.equal(ws[256 + 40:], sentinel[1])
+    # a pointer outside the workspace is refused, the error is parked (ctypes would swallow it) and re-raised by check()
+    ga.fn(ws.data_ptr() + 4096, 4, None, None)
+    refused = False
+    try:
+        ga.check()
+    except RuntimeError:
+        refused = True
+    q.put((rank, view.numpy().copy(), ok_bounds, refused, ga.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_graph_allreduce_hook_maps_pointers_into_the_workspace():
+    """Host side of `stemgnn_fwd_opts_t.graph_allreduce` (global-batch graph semantics for data-parallel runs)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_graph_allreduce_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(10, dtype=torch.float32) * 1.5).numpy()      # mean of 1x and 2x
+    for _, got, ok_bounds, refused, calls in out:
+        assert (got == want).all() and ok_bounds and refused and calls == 1
