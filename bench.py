@@ -10,8 +10,9 @@ Default workload = BASELINE.json configs[1], the shape the metric is quoted on: 
 
 Prints ONE JSON line.  Keys (see the task contract):
   value / ms_per_step   device-timed (CUDA events, L2 flushed between steps), inputs resident in HBM
-  e2e                   same metric through the public API with HOST buffers: pinned x -> H2D ->
-                        Model.forward -> D2H of the forecast, all inside the timed region
+  e2e                   same metric through the public API with HOST buffers, per step inside the timed region: pinned x ->
+                        H2D -> the captured forward -> D2H of the forecast -> synchronize, via Model.inference_session
+                        (stemgnn_b200/session.py); `plain_forward_loop` = the same with x.to(dev) -> Model.forward
   parity                "MAE vs ref" half of the metric: utils.math_utils.MAE and allclose(rtol 1e-3, atol 1e-4)
                         between this forward and the reference's CPU forward on the SAME inputs/weights
   roofline              the dominant kernel (GRU recurrence), timed live with CUDA events via the
