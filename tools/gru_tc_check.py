@@ -15,10 +15,20 @@ CASES = [(4, 40, 12), (8, 70, 12), (3, 53, 12), (7, 140, 8), (32, 140, 12), (32,
          (64, 228, 12), (33, 325, 28), (2, 448, 12)]
 
 
+def _host_gru(x_seq, p):
+    """ATen GRU on the host (1 layer, h0 = 0) with the model's weights: the comparison point of this tool.  (Plain torch — the
+    tools do not import oracle/.)"""
+    import torch
+    hidden = p["GRU.weight_hh_l0"].shape[1]
+    h0 = x_seq.new_zeros(1, x_seq.shape[1], hidden)
+    flat = [p["GRU.weight_ih_l0"], p["GRU.weight_hh_l0"], p["GRU.bias_ih_l0"], p["GRU.bias_hh_l0"]]
+    out, _ = torch._VF.gru(x_seq, h0, flat, True, 1, 0.0, False, False, False)
+    return out
+
+
 def one(B, N, W, path, reps):
     import torch
     from stemgnn_b200 import _lib as L, runtime, synthetic as sy
-    from oracle import torch_port as tp
     lib = L.load()
     dev = torch.device("cuda:0")
     p = sy.synthetic_params(N, W, 3, 5, seed=N, scale_mode="trained")
@@ -38,7 +48,7 @@ def one(B, N, W, path, reps):
     call(out.data_ptr())
     torch.cuda.synchronize()
     with torch.no_grad():
-        ref = tp._gru(x.permute(2, 0, 1).contiguous(), p)
+        ref = _host_gru(x.permute(2, 0, 1).contiguous(), p)
     rk = torch.einsum("sbh,s->bh", ref.double(), p["weight_key"][:, 0].double()).float()
     e_out = float((out.cpu() - ref).abs().max()); e_key = float((key.cpu() - rk).abs().max())
     msg = f"B={B} N={N} W={W} path={path}: max|gru_out err|={e_out:.3e} max|key err|={e_key:.3e}"
@@ -59,7 +69,6 @@ def stress(B, N, W, calls):
     """Race detector: `calls` independent forwards with gru_out, every result compared with the host GRU."""
     import torch
     from stemgnn_b200 import _lib as L, runtime, synthetic as sy
-    from oracle import torch_port as tp
     lib = L.load()
     dev = torch.device("cuda:0")
     p = sy.synthetic_params(N, W, 3, 5, seed=N, scale_mode="trained")
@@ -71,8 +80,8 @@ def stress(B, N, W, calls):
     xd = x.to(dev)
     key = torch.empty(B, N, device=dev); query = torch.empty(B, N, device=dev); out = torch.empty(N, B, N, device=dev)
     with torch.no_grad():
-        ref_cpu = tp._gru(x.permute(2, 0, 1).contiguous(), p)
-        ref64 = tp._gru(x.permute(2, 0, 1).contiguous().double(), {k: v.double() for k, v in p.items()})
+        ref_cpu = _host_gru(x.permute(2, 0, 1).contiguous(), p)
+        ref64 = _host_gru(x.permute(2, 0, 1).contiguous().double(), {k: v.double() for k, v in p.items()})
         ref = ref_cpu.to(dev)
     d = (ref_cpu.double() - ref64).abs()
     rows = sorted(set(int(v) for v in (d.amax(dim=(0, 2)) > 4e-6).nonzero().flatten()))
