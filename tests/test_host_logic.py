@@ -330,3 +330,23 @@ def test_runtime_cache_follows_replaced_parameters():
         assert m._runtime() is not r2
     finally:
         rt.build_ptrs = orig
+
+
+def test_interleaved_chebyshev_rows_make_gfted_rows_dense():
+    """The layout identity behind the coalesced graph-Fourier epilogue (csrc/spec_tc.cu): with the A-operand rows ordered
+    m' = node*3 + k', the chain's input G[(b*N + node)*3W + k'*W + t] is the dense array G[b][m'][t] of shape (B, 3N, W), and
+    the copy kernel's permutation (stack_n = N, row_mul = 3) produces exactly that row order from the stacked mul_L[1..3]."""
+    B, N, W = 3, 7, 4
+    for b in range(B):
+        for node in range(N):
+            for kp in range(3):
+                for t in range(W):
+                    assert (b * N + node) * 3 * W + kp * W + t == (b * 3 * N + node * 3 + kp) * W + t
+    rows = 3 * N
+    dst = {}
+    for r in range(rows):                      # pad_rows_kernel, stack_n > 0: r = k*stack_n + i -> i*row_mul + k + row_add
+        dst[(r % N) * 3 + r // N] = r
+    assert sorted(dst) == list(range(rows))
+    for node in range(N):
+        for kp in range(3):
+            assert dst[node * 3 + kp] == kp * N + node       # row node*3 + k' holds mul_L[k'+1][node][:]
